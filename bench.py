@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py - rendered audio seconds per second on BASELINE configs[1]
+(2 moving speakers x 6 mics x 40-point trajectory x 30 s @ 16 kHz, L = 4096 pre-baked RIRs).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on host cores
+
+One step = one pass of the hot path (SonicSim_moving.convolve_moving_receiver for both speakers)
+over a batch of U utterances per GPU.  `value` = whole-job mixture-seconds per second with inputs
+resident in HBM; `e2e` = the same through ss_render_host with pinned HOST buffers (H2D + D2H inside
+the timed region).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rendered_audio_seconds_per_second"
+UNIT = "audio-s/s"
+CFG = dict(P=40, C=6, L=4096, N=480000, sr=16000, speakers=2)
+
+
+def alg_bytes_moving(N, P, C, L):
+    """algorithmic HBM bytes of one moving source = 4 (N + P C L + C N)."""
+    return 4.0 * (N + P * C * L + C * N)
+
+
+def workload_name(U):
+    return ("cfg2: 2 moving speakers x 6-mic x 40-point trajectory x 30 s @16 kHz, L=4096 taps; "
+            "%d utterances per GPU per step" % U)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML every ~10 ms."""
+
+    def __init__(self, cuda_index):
+        self.samples = []
+        self.ok = False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            import torch
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.h = h
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:          # noqa: BLE001
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.ok:
+            self.th = threading.Thread(target=self._run, daemon=True)
+            self.th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.th.join(timeout=2)
+
+    def summary(self, windows):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        nv = self.nv
+        sel = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)] or self.samples
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+        reasons = sorted(k for k, bit in names.items() if any(s[2] & bit for s in sel))
+        return {"sm_mhz": float(np.median([s[1] for s in sel])) if sel else None,
+                "sm_max_mhz": float(self.max_sm), "reasons": reasons, "samples": len(sel),
+                "power_w_max": max([s[3] for s in sel]) if sel else None}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import cpu_bench
+    shape = (CFG["P"], CFG["C"], CFG["L"], CFG["N"])
+    pool = cpu_bench.CpuPool(shape=shape)           # includes each worker's own warm-up run
+    for _ in range(max(0, args.warmup - 1)):
+        pool.run_batch(1)
+    t_tot, units = 0.0, 0
+    for _ in range(args.steps):
+        t, u = pool.run_batch(1)
+        t_tot += t
+        units += u
+    pool.close()
+    secs = units / CFG["speakers"] * (CFG["N"] / CFG["sr"])
+    value = secs / t_tot
+    sample = "%d steps x %d sources (one per worker, 1 thread each) of cfg2 = %.0f mixture-seconds" % (
+        args.steps, pool.workers, secs)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(args.utterances)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": pool.workers, "kind": "port",
+                             "sample": sample,
+                             "note": "oracle port = the reference's own scipy.signal.oaconvolve + gather + lerp "
+                                     "(SonicSim_moving.py:86-94); the Python reference cannot travel to the GPU box"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def make_inputs(U, rank):
+    """U utterances x 2 speakers of cfg2; seeds 1000*cfg + item."""
+    from oracle import sonicsim_oracle as so          # synthetic-input generators only
+    from sonicsim_b200 import render
+    items = []
+    for u in range(U * CFG["speakers"]):
+        seed = 2000 + rank * 100000 + u
+        rng = np.random.default_rng(seed)
+        x = so.synth_dry(rng, CFG["N"])
+        h = so.synth_rirs(rng, CFG["P"], CFG["C"], CFG["L"])
+        pos = so.synth_path(rng, CFG["P"])
+        np.random.seed(seed % (2 ** 31))
+        b = render.trajectory_bounds(pos, CFG["N"])
+        items.append((x, h, b))
+    return items
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from sonicsim_b200 import render, shard
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    U, K, W = args.utterances, args.steps, args.warmup
+    R = render.Renderer(local_rank)
+    items = make_inputs(U, rank)
+    n_src = len(items)
+    C, N = CFG["C"], CFG["N"]
+
+    # ---- device-resident arm
+    d_srcs = [render.MovingSource(torch.from_numpy(x).to(dev), torch.from_numpy(h).to(dev), torch.from_numpy(b).to(dev))
+              for x, h, b in items]
+    d_outs = [torch.empty((C, N), dtype=torch.float32, device=dev) for _ in range(n_src)]
+    step_alg = sum(alg_bytes_moving(N, CFG["P"], C, CFG["L"]) for _ in items)
+    step_audio = U * N / CFG["sr"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(W):
+        R.render_device(d_srcs, d_outs)
+    barrier()
+    R.reset_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_w0 = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        R.render_device(d_srcs, d_outs)
+    e1.record()
+    barrier()
+    t_w1 = time.perf_counter()
+    launches = R.launch_count()
+    dev_s = e0.elapsed_time(e1) / 1e3
+
+    # ---- per-kernel timing (same K steps again, CUDA events around every launch)
+    R.set_profiling(True)
+    for _ in range(K):
+        R.render_device(d_srcs, d_outs)
+    torch.cuda.synchronize()
+    ms_spec, ms_rend, n_pairs = R.get_profile()
+    R.set_profiling(False)
+
+    # ---- end-to-end arm: pinned host buffers through ss_render_host
+    h_items = [(torch.from_numpy(x).pin_memory(), torch.from_numpy(h).pin_memory(), b) for x, h, b in items]
+    h_srcs = [render.MovingSource(x.numpy(), h.numpy(), b) for x, h, b in h_items]
+    h_outs_t = [torch.empty((C, N), dtype=torch.float32).pin_memory() for _ in range(n_src)]
+    h_outs = [t.numpy() for t in h_outs_t]
+    for _ in range(max(1, min(W, 2))):
+        R.render_host(h_srcs, h_outs)
+    barrier()
+    t_e0 = time.perf_counter()
+    for _ in range(K):
+        R.render_host(h_srcs, h_outs)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t_e0
+    barrier()
+    t_e1 = time.perf_counter()
+    sampler.stop()
+    # the device arm and the host arm must agree bit for bit (same kernels)
+    same = bool(np.array_equal(h_outs[0], d_outs[0].cpu().numpy()))
+    checksum = float(np.abs(h_outs[-1]).sum())          # the D2H'd result is really read
+
+    # ---- max over ranks (device time), counters all-gather (the path's only collective)
+    tt = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_max, e2e_max = float(tt[0]), float(tt[1])
+    counters = shard.gather_counters(step_audio * K, dev_s, step_alg * K, device=dev)
+    total_audio = float(counters[:, 0].sum())
+    value = total_audio / dev_max
+    e2e_value = total_audio / e2e_max
+
+    if rank == 0:
+        peaks, peak_src = {}, "fallback (B200_PROFILING.md: 6650 GB/s)"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        k_render_s = ms_rend / 1e3 / max(n_pairs, 1)
+        k_spec_s = ms_spec / 1e3 / max(n_pairs, 1)
+        alg_per_launch = step_alg * K / max(n_pairs, 1)
+        achieved = alg_per_launch / k_render_s / 1e9 if k_render_s > 0 else 0.0
+        achieved_path = alg_per_launch / (k_render_s + k_spec_s) / 1e9 if k_render_s > 0 else 0.0
+        in_b = sum(x.nbytes + h.nbytes + b.nbytes for x, h, b in items)
+        out_b = n_src * C * N * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * dev_max / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(U), "utterances_per_gpu_per_step": U,
+                       "sources_per_gpu_per_step": n_src,
+                       "l2": "inputs %.0f MB + outputs %.0f MB per step are larger than the 126 MB L2 (no flush needed)"
+                             % (in_b / 1e6, out_b / 1e6),
+                       "parallelism": "units sharded across %d rank(s), no data-path collective" % world},
+            "clocks": sampler.summary([(t_w0, t_w1), (t_e0, t_e1)]),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_b), "d2h_bytes_per_step": int(out_b),
+                    "ms_per_step": 1e3 * e2e_max / K, "api": "sonicsim_b200.render.Renderer.render_host -> ss_render_host",
+                    "bit_identical_to_device_arm": same, "checksum": checksum},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "alg_bytes_per_launch": alg_per_launch, "kernel_ms": 1e3 * k_render_s,
+                         "k_spectra_ms": 1e3 * k_spec_s, "path_achieved": achieved_path,
+                         "path_frac": achieved_path / peak, "launch_pairs_timed": int(n_pairs),
+                         "timing": "CUDA events recorded by the library on the launching stream around every "
+                                   "k_spectra / k_render launch, K steps repeated right after the timed region"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import cpu_bench
+            shape = (CFG["P"], CFG["C"], CFG["L"], CFG["N"])
+            t1 = cpu_bench.single_thread_time(shape, reps=1)
+            pool = cpu_bench.CpuPool(shape=shape)
+            t, units = pool.run_batch(args.cpu_reps)
+            pool.close()
+            secs = units / CFG["speakers"] * (N / CFG["sr"])
+            line["cpu_baseline"] = {
+                "value": secs / t, "unit": UNIT, "cores": pool.workers, "kind": "port",
+                "sample": "%d cfg2 sources (one per worker process, 1 thread each, %d rep) = %.0f mixture-seconds in %.1f s"
+                          % (units, args.cpu_reps, secs, t),
+                "single_thread_value": (N / CFG["sr"]) / CFG["speakers"] / t1,
+                "host_cpu_count": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utterances", type=int, default=16, help="utterances per GPU per step")
+    ap.add_argument("--cpu-reps", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+/* sonicsim_b200.h - C ABI of the B200-native moving-source renderer.
+ *
+ * The reference (JusperLee/SonicSim) has no FFI layer: its hot path is module-level Python
+ * (SonicSim-SonicSet/SonicSim_moving.py, SonicSim_audio.py) called positionally from
+ * SonicSet.py:77-101.  This header is the native boundary a maintainer binds instead (ctypes stub
+ * in INTEGRATION.md; sonicsim_b200/_lib.py is that stub).  Each entry point names the reference
+ * function(s) it replaces.  Plain pointers and sizes only; no torch / Python types.
+ *
+ * Conventions
+ *   - float32 everywhere, row-major.  dry x: (N,), RIRs: (P, C, L), output: (C, N) channel-major.
+ *   - `*_dev` entry points take DEVICE pointers and enqueue work on `stream` (a cudaStream_t cast to
+ *     void*; NULL = legacy default stream) without synchronising.
+ *   - `*_host` entry points take HOST pointers (pinned memory gives full PCIe rate), copy in,
+ *     render and copy out; they return after the results are in host memory.
+ *   - every function returns 0 (SS_OK) or a negative ss_status; ss_strerror() describes it.  The
+ *     Python shim turns these into the exception types the reference raises (IndexError /
+ *     ValueError), see INTEGRATION.md.
+ */
+#ifndef SONICSIM_B200_H_
+#define SONICSIM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ss_ctx ss_ctx;
+
+typedef enum {
+    SS_OK = 0,
+    SS_ERR_INVALID = -1,      /* bad argument (null pointer, non-positive size, unknown mode)       */
+    SS_ERR_INDEX = -2,        /* trajectory refers to a position >= P - 1 (reference: IndexError)   */
+    SS_ERR_CUDA = -3,         /* CUDA runtime error; ss_last_cuda_error() has the code              */
+    SS_ERR_NOMEM = -4,        /* device or pinned allocation failed                                 */
+    SS_ERR_UNSUPPORTED = -5   /* shape outside what this build handles                              */
+} ss_status;
+
+/* how one source's trajectory is given */
+typedef enum {
+    SS_STATIC = 0,            /* P == 1, no interpolation: convolve_fixed_receiver                  */
+    SS_MOVING_BOUNDS = 1,     /* `bounds`: P int32 cumulative segment bounds, bounds[0]=0, [P-1]=N   */
+    SS_MOVING_INDEXED = 2     /* `idx` (int32, N) and `w` (float32, N): interp_index / interp_weight */
+} ss_mode;
+
+/* One (utterance, source) unit of work = one call of convolve_moving_receiver /
+ * convolve_fixed_receiver in the reference.  Pointers are device pointers for ss_render_dev and
+ * host pointers for ss_render_host. */
+typedef struct {
+    const float* x;           /* (N,)       dry source, SonicSim_moving.py:64                        */
+    const float* rir;         /* (P, C, L)  per-position RIRs, SonicSim_moving.py:65; (C, L) if static */
+    float* out;               /* (C, N)     rendered stem, SonicSim_moving.py:96 / :60               */
+    const int32_t* bounds;    /* SS_MOVING_BOUNDS: np.cumsum(samples_per_interval) with leading 0    */
+    const int32_t* idx;       /* SS_MOVING_INDEXED: interp_index (SonicSim_moving.py:42)             */
+    const float* w;           /* SS_MOVING_INDEXED: interp_weight (SonicSim_moving.py:43)            */
+    int32_t N, P, C, L;
+    int32_t mode;             /* ss_mode */
+    int32_t reserved;
+} ss_source;
+
+/* library / build identification */
+int ss_version(void);
+const char* ss_strerror(int status);
+int ss_last_cuda_error(void);
+
+/* One context per process per GPU: owns the twiddle table, scratch for spectra and the staging
+ * buffers / streams of the host path.  `device` is the CUDA ordinal (after CUDA_VISIBLE_DEVICES). */
+int ss_create(int device, ss_ctx** out);
+void ss_destroy(ss_ctx* ctx);
+
+/* Tunables: scratch budget per launch group (bytes of spectra kept live, sized to stay in L2). */
+int ss_set_chunk_bytes(ss_ctx* ctx, int64_t bytes);
+
+/* Replaces SonicSim_moving.convolve_moving_receiver (SonicSim_moving.py:63-96) and
+ * convolve_fixed_receiver (:47-61) for a whole batch of sources in three kernel launches per
+ * chunk.  Device pointers; asynchronous on `stream`. */
+int ss_render_dev(ss_ctx* ctx, const ss_source* items, int n_items, void* stream);
+
+/* Same, host pointers: H2D -> render -> D2H, pipelined over chunks on internal streams.  Returns
+ * when every `out` is complete.  This is what the drop-in Python functions call. */
+int ss_render_host(ss_ctx* ctx, const ss_source* items, int n_items);
+
+/* Single-source conveniences with the argument order of the reference functions. */
+int ss_convolve_fixed_receiver(ss_ctx* ctx, const float* source_audio, const float* rirs, float* out,
+                               int32_t N, int32_t C, int32_t L);                        /* :47-61 */
+int ss_convolve_moving_receiver(ss_ctx* ctx, const float* source_audio, const float* rirs,
+                                const int32_t* interp_index, const float* interp_weight, float* out,
+                                int32_t N, int32_t P, int32_t C, int32_t L);            /* :63-96 */
+
+/* Counters since ss_create / ss_reset_stats: kernels launched and device time is NOT measured
+ * here (bench.py uses CUDA events); this is the launch count bench.py reports as gpu_launches. */
+int64_t ss_launch_count(const ss_ctx* ctx);
+void ss_reset_stats(ss_ctx* ctx);
+
+/* Per-kernel device timing with CUDA events recorded on the launching stream around k_spectra and
+ * k_render (bench.py's roofline numbers).  ss_get_profile waits for the recorded launches, returns
+ * the summed milliseconds of each kernel and the number of (k_spectra, k_render) launch pairs since
+ * the previous call, and clears the record. */
+int ss_set_profiling(ss_ctx* ctx, int on);
+int ss_get_profile(ss_ctx* ctx, double* ms_spectra, double* ms_render, int64_t* n_pairs);
+
+/* pinned host memory helpers (cudaHostAlloc) for callers without torch */
+int ss_host_alloc(void** ptr, int64_t bytes);
+void ss_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SONICSIM_B200_H_ */

@@ -1,0 +1,113 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference functions
+(/root/reference/SonicSim-SonicSet/SonicSim_moving.py:15-125, SonicSim_audio.py:17-47)
+on seeded synthetic inputs.  Run in the authoring container only:
+
+    python oracle/make_golden.py
+
+The fixtures hold both the inputs and the reference's outputs, so the tests that read
+them need neither /root/reference nor this script.  TEST INFRASTRUCTURE.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader                      # noqa: E402
+from oracle import sonicsim_oracle as so           # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    import torch
+    ref, ref_audio = ref_loader.load(want_audio=True)
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- a1: setup_dynamic_interp (seed np.random right before the call)
+    cases = {}
+    for k, (seed, P, N) in enumerate([(11, 5, 1000), (12, 40, 48000), (13, 3, 7), (14, 9, 5),
+                                      (15, 2, 333)]):
+        rng = np.random.default_rng(seed)
+        pos = so.synth_path(rng, P)
+        if k == 1:
+            pos[7] = pos[6]                         # duplicate waypoint -> zero-length segment
+        np.random.seed(seed)
+        idx, w = ref.setup_dynamic_interp(pos, N)
+        cases[f"pos{k}"] = pos
+        cases[f"N{k}"] = np.int64(N)
+        cases[f"seed{k}"] = np.int64(seed)
+        cases[f"idx{k}"] = idx.astype(np.int32)
+        cases[f"w{k}"] = w
+    cases["n_cases"] = np.int64(5)
+    np.savez_compressed(os.path.join(OUT, "setup_dynamic_interp.npz"), **cases)
+
+    # ---- a4: convolve_fixed_receiver
+    cases = {}
+    for k, (seed, C, L, N) in enumerate([(21, 1, 300, 2000), (22, 2, 1025, 9000), (23, 3, 64, 50),
+                                         (24, 2, 5000, 4500)]):
+        rng = np.random.default_rng(seed)
+        x = so.synth_dry(rng, N).reshape(1, N)
+        h = so.synth_rirs(rng, 1, C, L)[0]
+        y = ref.convolve_fixed_receiver(x, h)
+        y_t = ref.convolve_fixed_receiver(torch.from_numpy(x), torch.from_numpy(h))   # SonicSet.py:93 passes tensors
+        assert np.array_equal(np.asarray(y), np.asarray(y_t))
+        cases[f"x{k}"], cases[f"h{k}"], cases[f"y{k}"] = x, h, np.asarray(y, dtype=np.float32)
+        assert y.dtype == np.float32
+    cases["n_cases"] = np.int64(4)
+    np.savez_compressed(os.path.join(OUT, "convolve_fixed_receiver.npz"), **cases)
+
+    # ---- a2: convolve_moving_receiver with the reference's own (idx, w)
+    cases = {}
+    for k, (seed, P, C, L, N) in enumerate([(31, 5, 2, 257, 6000), (32, 2, 1, 100, 1500),
+                                            (33, 7, 3, 2100, 4000),      # L >= N/2: oaconvolve falls back to fftconvolve
+                                            (34, 12, 2, 4500, 20000),    # L > 4096: two partitions in the CUDA path
+                                            (35, 6, 2, 31, 9)]):         # N < typical block, tiny
+        rng = np.random.default_rng(seed)
+        x = so.synth_dry(rng, N)
+        h = so.synth_rirs(rng, P, C, L)
+        pos = so.synth_path(rng, P)
+        np.random.seed(seed)
+        idx, w = ref.setup_dynamic_interp(pos, N)
+        y = ref.convolve_moving_receiver(x, h, idx, w)
+        assert y.dtype == np.float32, y.dtype
+        cases[f"x{k}"], cases[f"h{k}"] = x, h
+        cases[f"idx{k}"], cases[f"w{k}"] = idx.astype(np.int32), w
+        cases[f"y{k}"] = y
+    cases["n_cases"] = np.int64(5)
+    np.savez_compressed(os.path.join(OUT, "convolve_moving_receiver.npz"), **cases)
+
+    # ---- a3: interpolate_moving_audio (torch in, torch out, RNG seeded before the call)
+    cases = {}
+    for k, (seed, P, C, L, N) in enumerate([(41, 6, 2, 400, 8000), (42, 4, 1, 1000, 5000)]):
+        rng = np.random.default_rng(seed)
+        x = so.synth_dry(rng, N).reshape(1, N)
+        h = so.synth_rirs(rng, P, C, L).reshape(P, 1, C, L)
+        pos = so.synth_path(rng, P)
+        np.random.seed(seed)
+        y = ref.interpolate_moving_audio(torch.from_numpy(x), torch.from_numpy(h), [list(p) for p in pos])
+        assert isinstance(y, torch.Tensor) and y.dtype == torch.float32
+        cases[f"x{k}"], cases[f"h{k}"], cases[f"pos{k}"] = x, h, pos
+        cases[f"seed{k}"] = np.int64(seed)
+        cases[f"y{k}"] = y.numpy()
+    cases["n_cases"] = np.int64(2)
+    np.savez_compressed(os.path.join(OUT, "interpolate_moving_audio.npz"), **cases)
+
+    # ---- a6: fft_conv (torch.fft)
+    cases = {}
+    for k, (seed, L, N) in enumerate([(51, 200, 3000), (52, 4096, 6000)]):
+        rng = np.random.default_rng(seed)
+        x = so.synth_dry(rng, N)
+        h = so.synth_rirs(rng, 1, 1, L)[0, 0]
+        y = ref_audio.fft_conv(torch.from_numpy(x), torch.from_numpy(h), is_cpu=True)
+        cases[f"x{k}"], cases[f"h{k}"], cases[f"y{k}"] = x, h, y.numpy()
+    cases["n_cases"] = np.int64(2)
+    np.savez_compressed(os.path.join(OUT, "fft_conv.npz"), **cases)
+
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,503 @@
+// sonicsim_b200 :: ss_kernels.cu  -  sm_100a kernels + the C ABI of include/sonicsim_b200.h
+//
+// Path:  SonicSim_moving.convolve_moving_receiver (SonicSim_moving.py:63-96) and
+// convolve_fixed_receiver (:47-61), restructured as a uniformly partitioned overlap-save
+// convolution in the segment-local form
+//      y[c,n] = sum_p hat_p(n) (x * h[p,c])[n],     hat_p = linear hat over segments p-1, p,
+// so only the two positions a sample needs are ever convolved (2/P of the reference's work) and the
+// (P, C, N) intermediate of :86 is never materialised.
+//
+// Three launches per chunk of sources:
+//   k_spectra : real rows (RIR partitions, dry windows) -> half spectra (two rows per complex FFT)
+//   k_render  : per (block, channel): Z = sum_part X[b-part] (H[p] + i H[p+1]); one 8192-point
+//               inverse FFT in shared memory gives both positions' convolutions as Re / Im; the
+//               closing radix-2 is fused with the per-sample lerp and the (C, N) store.
+// fp32 throughout (the reference is float32 end to end), no cuFFT.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/sonicsim_b200.h"
+#include "ss_phases.cuh"
+
+using namespace ss;
+
+__device__ float2 g_tw[kF];          // exp(-2 pi i m / 8192), filled from the host in double precision
+
+// ----------------------------------------------------------------------------- k_spectra
+__global__ void __launch_bounds__(kThreads, 2)
+k_spectra(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_src) {
+    extern __shared__ float2 smem[];
+    const int t = threadIdx.x;
+    const int si = find_source(prefix, n_src, blockIdx.x);
+    const Source& S = srcs[si];
+    int local = blockIdx.x - prefix[si];
+    Row ra, rb;
+    const int nh = spectra_pairs_h(S);
+    if (local < nh) { ra = make_row_h(S, 2 * local); rb = make_row_h(S, 2 * local + 1); }
+    else { local -= nh; ra = make_row_x(S, 2 * local); rb = make_row_x(S, 2 * local + 1); }
+
+    Regs32 R;
+    spectra_phase1(t, ra, rb, smem);
+    __syncthreads();
+    load2(t, smem, R);
+    __syncthreads();
+    passB2<false>(t, smem, R, g_tw);
+    __syncthreads();
+    load2(t, smem, R);
+    spectra_phase3_compute(t, R, g_tw);
+    __syncthreads();
+    spectra_phase3_store(t, smem, R);
+    __syncthreads();
+    spectra_phase4(t, smem, ra, rb);
+}
+
+// ----------------------------------------------------------------------------- k_render
+__global__ void __launch_bounds__(kThreads, 2)
+k_render(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_src) {
+    extern __shared__ float2 smem[];
+    __shared__ int s_red[2 * (kThreads / 32)];
+    const int t = threadIdx.x;
+    const int si = find_source(prefix, n_src, blockIdx.x);
+    const Source& S = srcs[si];
+    const int local = blockIdx.x - prefix[si];
+    const float g = S.gain ? *S.gain : 1.0f;
+    Regs32 R;
+
+    if (S.mode == MODE_STATIC) {
+        const int ncp = (S.C + 1) >> 1;
+        const int b = local / ncp, cp = local - b * ncp;
+        const int c0 = 2 * cp, c1 = c0 + 1;
+        const int n0 = b * kB;
+        const float2* X0 = S.xspec + (size_t)b * kSpec;
+        const float2* Hp = S.hspec + (size_t)c0 * S.K * kSpec;
+        const float2* Hq = (c1 < S.C) ? S.hspec + (size_t)c1 * S.K * kSpec : nullptr;
+        form_z(t, X0, b, S.K, Hp, Hq, R);
+        render_phase1(t, smem, R);
+        __syncthreads();
+        load2(t, smem, R);
+        __syncthreads();
+        passB2<true>(t, smem, R, g_tw);
+        __syncthreads();
+        load2(t, smem, R);
+        // static: Re -> channel c0, Im -> channel c1
+        passC_compute<true>(t, R.a, g_tw);
+        passC_compute<true>(t + 256, R.b, g_tw);
+        const float2 wt = dirw<true>(g_tw[t]);
+        float* o0 = S.out + (size_t)c0 * S.N;
+        float* o1 = S.out + (size_t)(c1 < S.C ? c1 : c0) * S.N;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int sl = out16(r);
+            float2 z = csub(R.a[sl], cmul(R.b[sl], final_twiddle<true>(t, r, wt)));
+            int n = n0 + t + 256 * r;
+            if (n < S.N) {
+                o0[n] = z.x * g;
+                if (c1 < S.C) o1[n] = z.y * g;
+            }
+        }
+        return;
+    }
+
+    // moving source: one channel per CTA
+    const int b = local / S.C, c = local - b * S.C;
+    const int n0 = b * kB;
+    float acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+    int p_lo, p_hi;
+    if (S.mode == MODE_MOVING_BOUNDS) {
+        const int n_last = (n0 + kB < S.N ? n0 + kB : S.N) - 1;
+        p_lo = seg_of(S.bounds, S.P - 1, n0);
+        p_hi = seg_of(S.bounds, S.P - 1, n_last) + 1;
+    } else {
+        int pmin, pmax;
+        idx_range(t, n0, S, pmin, pmax);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            int a = __shfl_xor_sync(0xffffffffu, pmin, o), bmax = __shfl_xor_sync(0xffffffffu, pmax, o);
+            pmin = a < pmin ? a : pmin; pmax = bmax > pmax ? bmax : pmax;
+        }
+        if ((t & 31) == 0) { s_red[t >> 5] = pmin; s_red[8 + (t >> 5)] = pmax; }
+        __syncthreads();
+        pmin = s_red[0]; pmax = s_red[8];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { pmin = s_red[i] < pmin ? s_red[i] : pmin; pmax = s_red[8 + i] > pmax ? s_red[8 + i] : pmax; }
+        // the reference raises IndexError for idx + 1 >= P (checked on the host path); clamp here
+        p_lo = pmin < 0 ? 0 : pmin;
+        p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
+    }
+    const float2* X0 = S.xspec + (size_t)b * kSpec;
+    for (int p = p_lo; p <= p_hi; p += 2) {
+        const float2* Hp = S.hspec + ((size_t)p * S.C + c) * S.K * kSpec;
+        const float2* Hq = (p + 1 <= p_hi) ? S.hspec + ((size_t)(p + 1) * S.C + c) * S.K * kSpec : nullptr;
+        form_z(t, X0, b, S.K, Hp, Hq, R);
+        render_phase1(t, smem, R);
+        __syncthreads();
+        load2(t, smem, R);
+        __syncthreads();
+        passB2<true>(t, smem, R, g_tw);
+        __syncthreads();
+        load2(t, smem, R);
+        __syncthreads();          // next iteration's pass A overwrites smem
+        if (S.mode == MODE_MOVING_BOUNDS) { BoundsWeights wf(S, n0, t, p); render_phase3(t, R, g_tw, acc, wf); }
+        else { IndexedWeights wf(S, n0, t, p); render_phase3(t, R, g_tw, acc, wf); }
+    }
+    store_block(t, n0, S, S.out + (size_t)c * S.N, acc, g);
+}
+
+// ============================================================================= host side
+struct ss_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int64_t chunk_bytes = 48ll << 20;
+    // scratch for spectra
+    char* d_scratch = nullptr; size_t scratch_cap = 0;
+    // descriptor ring (pinned host + device)
+    static const int kRing = 4;
+    char* h_desc[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    char* d_desc[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    size_t desc_cap[kRing] = {0, 0, 0, 0};
+    cudaEvent_t desc_ev[kRing];
+    int ring_pos = 0;
+    // host path
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    struct Slot { char* d_in = nullptr; size_t in_cap = 0; char* d_out = nullptr; size_t out_cap = 0;
+                  cudaEvent_t ev_in, ev_done, ev_free; } slot[2];
+    int64_t launches = 0;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool profiling = false;
+    struct Prof { cudaEvent_t e0, e1, e2; };
+    std::vector<Prof> prof;
+};
+
+static thread_local int g_last_cuda = 0;
+#define CK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_last_cuda = (int)e_; \
+    return e_ == cudaErrorMemoryAllocation ? SS_ERR_NOMEM : SS_ERR_CUDA; } } while (0)
+
+extern "C" int ss_version(void) { return 100; }
+extern "C" int ss_last_cuda_error(void) { return g_last_cuda; }
+extern "C" const char* ss_strerror(int st) {
+    switch (st) {
+        case SS_OK: return "ok";
+        case SS_ERR_INVALID: return "invalid argument";
+        case SS_ERR_INDEX: return "index out of bounds: trajectory refers to position >= P - 1";
+        case SS_ERR_CUDA: return "CUDA runtime error";
+        case SS_ERR_NOMEM: return "out of device / pinned memory";
+        case SS_ERR_UNSUPPORTED: return "unsupported shape";
+        default: return "unknown status";
+    }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int ss_create(int device, ss_ctx** out) {
+    if (!out) return SS_ERR_INVALID;
+    CK(cudaSetDevice(device));
+    ss_ctx* c = new ss_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    std::vector<float2> tw(kF);
+    for (int m = 0; m < kF; ++m) {
+        double a = -2.0 * M_PI * (double)m / (double)kF;
+        tw[m] = make_float2((float)cos(a), (float)sin(a));
+    }
+    CK(cudaMemcpyToSymbol(g_tw, tw.data(), sizeof(float2) * kF));
+    const int smem = kPadF * (int)sizeof(float2);
+    CK(cudaFuncSetAttribute(k_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int i = 0; i < ss_ctx::kRing; ++i) CK(cudaEventCreateWithFlags(&c->desc_ev[i], cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&c->slot[i].ev_in, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->slot[i].ev_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->slot[i].ev_free, cudaEventDisableTiming));
+    }
+    *out = c;
+    return SS_OK;
+}
+
+extern "C" void ss_destroy(ss_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    for (int i = 0; i < ss_ctx::kRing; ++i) {
+        if (c->h_desc[i]) cudaFreeHost(c->h_desc[i]);
+        if (c->d_desc[i]) cudaFree(c->d_desc[i]);
+        cudaEventDestroy(c->desc_ev[i]);
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (c->slot[i].d_in) cudaFree(c->slot[i].d_in);
+        if (c->slot[i].d_out) cudaFree(c->slot[i].d_out);
+        cudaEventDestroy(c->slot[i].ev_in); cudaEventDestroy(c->slot[i].ev_done); cudaEventDestroy(c->slot[i].ev_free);
+    }
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    delete c;
+}
+
+extern "C" int ss_set_chunk_bytes(ss_ctx* c, int64_t bytes) {
+    if (!c || bytes < (1 << 20)) return SS_ERR_INVALID;
+    c->chunk_bytes = bytes;
+    return SS_OK;
+}
+extern "C" int64_t ss_launch_count(const ss_ctx* c) { return c ? c->launches : 0; }
+extern "C" void ss_reset_stats(ss_ctx* c) { if (c) c->launches = 0; }
+
+extern "C" int ss_set_profiling(ss_ctx* c, int on) {
+    if (!c) return SS_ERR_INVALID;
+    c->profiling = on != 0;
+    return SS_OK;
+}
+// Sum of per-launch device times since the last call (waits for the recorded work to finish).
+extern "C" int ss_get_profile(ss_ctx* c, double* ms_spectra, double* ms_render, int64_t* n_pairs) {
+    if (!c) return SS_ERR_INVALID;
+    double a = 0, b = 0;
+    for (auto& pf : c->prof) {
+        CK(cudaEventSynchronize(pf.e2));
+        float t1 = 0, t2 = 0;
+        CK(cudaEventElapsedTime(&t1, pf.e0, pf.e1));
+        CK(cudaEventElapsedTime(&t2, pf.e1, pf.e2));
+        a += t1; b += t2;
+        cudaEventDestroy(pf.e0); cudaEventDestroy(pf.e1); cudaEventDestroy(pf.e2);
+    }
+    if (ms_spectra) *ms_spectra = a;
+    if (ms_render) *ms_render = b;
+    if (n_pairs) *n_pairs = (int64_t)c->prof.size();
+    c->prof.clear();
+    return SS_OK;
+}
+
+extern "C" int ss_host_alloc(void** p, int64_t bytes) {
+    if (!p || bytes <= 0) return SS_ERR_INVALID;
+    CK(cudaHostAlloc(p, (size_t)bytes, cudaHostAllocDefault));
+    return SS_OK;
+}
+extern "C" void ss_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+static int validate_item(const ss_source& it) {
+    if (!it.x || !it.rir || !it.out) return SS_ERR_INVALID;
+    if (it.N <= 0 || it.C <= 0 || it.L <= 0 || it.P <= 0) return SS_ERR_INVALID;
+    if (it.mode == SS_STATIC) { if (it.P != 1) return SS_ERR_INVALID; }
+    else if (it.mode == SS_MOVING_BOUNDS) { if (it.P < 2 || !it.bounds) return SS_ERR_INVALID; }
+    else if (it.mode == SS_MOVING_INDEXED) { if (it.P < 2 || !it.idx || !it.w) return SS_ERR_INVALID; }
+    else return SS_ERR_INVALID;
+    return SS_OK;
+}
+static size_t spectra_bytes(const ss_source& it) {
+    size_t K = (it.L + kB - 1) / kB, nb = (it.N + kB - 1) / kB;
+    return ((size_t)it.P * it.C * K + nb) * kSpec * sizeof(float2);
+}
+
+// Enqueue the three launches for items[first, last) (device pointers) on `stream`.
+static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, cudaStream_t stream) {
+    const int n = last - first;
+    size_t need = 0;
+    for (int i = first; i < last; ++i) need += spectra_bytes(items[i]);
+    if (need > c->scratch_cap) {
+        CK(cudaDeviceSynchronize());
+        if (c->d_scratch) CK(cudaFree(c->d_scratch));
+        c->d_scratch = nullptr; c->scratch_cap = 0;
+        size_t cap = align_up(need + need / 4, 1 << 20);
+        CK(cudaMalloc(&c->d_scratch, cap));
+        c->scratch_cap = cap;
+    }
+    // descriptor block: Source[n] | prefix_spec[n+1] | prefix_render[n+1]
+    const size_t off_ps = align_up(sizeof(Source) * n, 16);
+    const size_t off_pr = off_ps + align_up(sizeof(int) * (n + 1), 16);
+    const size_t bytes = off_pr + align_up(sizeof(int) * (n + 1), 16);
+    const int slot = c->ring_pos; c->ring_pos = (c->ring_pos + 1) % ss_ctx::kRing;
+    if (bytes > c->desc_cap[slot]) {
+        CK(cudaEventSynchronize(c->desc_ev[slot]));
+        if (c->h_desc[slot]) CK(cudaFreeHost(c->h_desc[slot]));
+        if (c->d_desc[slot]) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->d_desc[slot])); }
+        c->h_desc[slot] = nullptr; c->d_desc[slot] = nullptr; c->desc_cap[slot] = 0;
+        size_t cap = align_up(bytes * 2, 4096);
+        CK(cudaHostAlloc((void**)&c->h_desc[slot], cap, cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&c->d_desc[slot], cap));
+        c->desc_cap[slot] = cap;
+    } else {
+        CK(cudaEventSynchronize(c->desc_ev[slot]));
+    }
+    Source* hs = (Source*)c->h_desc[slot];
+    int* hps = (int*)(c->h_desc[slot] + off_ps);
+    int* hpr = (int*)(c->h_desc[slot] + off_pr);
+    char* scratch = c->d_scratch;
+    int ps = 0, pr = 0;
+    for (int i = 0; i < n; ++i) {
+        const ss_source& it = items[first + i];
+        Source s;
+        memset(&s, 0, sizeof(s));
+        s.x = it.x; s.rir = it.rir; s.out = it.out;
+        s.bounds = it.mode == SS_MOVING_BOUNDS ? it.bounds : nullptr;
+        s.idx = it.mode == SS_MOVING_INDEXED ? it.idx : nullptr;
+        s.w = it.mode == SS_MOVING_INDEXED ? it.w : nullptr;
+        s.gain = nullptr;
+        s.N = it.N; s.P = it.P; s.C = it.C; s.L = it.L;
+        s.K = (it.L + kB - 1) / kB; s.nb = (it.N + kB - 1) / kB;
+        s.mode = it.mode;
+        s.hspec = (float2*)scratch; scratch += (size_t)s.P * s.C * s.K * kSpec * sizeof(float2);
+        s.xspec = (float2*)scratch; scratch += (size_t)s.nb * kSpec * sizeof(float2);
+        hs[i] = s;
+        hps[i] = ps; hpr[i] = pr;
+        ps += spectra_pairs_h(s) + spectra_pairs_x(s);
+        pr += render_ctas(s);
+    }
+    hps[n] = ps; hpr[n] = pr;
+    CK(cudaMemcpyAsync(c->d_desc[slot], c->h_desc[slot], bytes, cudaMemcpyHostToDevice, stream));
+    CK(cudaEventRecord(c->desc_ev[slot], stream));
+    const Source* ds = (const Source*)c->d_desc[slot];
+    const int* dps = (const int*)(c->d_desc[slot] + off_ps);
+    const int* dpr = (const int*)(c->d_desc[slot] + off_pr);
+    const int smem = kPadF * (int)sizeof(float2);
+    ss_ctx::Prof pf;
+    if (c->profiling) {
+        CK(cudaEventCreate(&pf.e0)); CK(cudaEventCreate(&pf.e1)); CK(cudaEventCreate(&pf.e2));
+        CK(cudaEventRecord(pf.e0, stream));
+    }
+    k_spectra<<<ps, kThreads, smem, stream>>>(ds, dps, n);
+    CK(cudaGetLastError());
+    if (c->profiling) CK(cudaEventRecord(pf.e1, stream));
+    k_render<<<pr, kThreads, smem, stream>>>(ds, dpr, n);
+    CK(cudaGetLastError());
+    if (c->profiling) { CK(cudaEventRecord(pf.e2, stream)); c->prof.push_back(pf); }
+    c->launches += 2;
+    return SS_OK;
+}
+
+// split [0, n) into chunks whose spectra fit the L2-sized budget
+static void make_chunks(const ss_ctx* c, const ss_source* items, int n, std::vector<int>& cuts) {
+    cuts.clear(); cuts.push_back(0);
+    size_t acc = 0;
+    for (int i = 0; i < n; ++i) {
+        size_t sb = spectra_bytes(items[i]);
+        if (i > cuts.back() && acc + sb > (size_t)c->chunk_bytes) { cuts.push_back(i); acc = 0; }
+        acc += sb;
+    }
+    cuts.push_back(n);
+}
+
+extern "C" int ss_render_dev(ss_ctx* c, const ss_source* items, int n_items, void* stream) {
+    if (!c || (!items && n_items > 0) || n_items < 0) return SS_ERR_INVALID;
+    if (n_items == 0) return SS_OK;
+    CK(cudaSetDevice(c->device));
+    for (int i = 0; i < n_items; ++i) { int st = validate_item(items[i]); if (st) return st; }
+    std::vector<int> cuts;
+    make_chunks(c, items, n_items, cuts);
+    for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+        int st = launch_chunk(c, items, cuts[k], cuts[k + 1], (cudaStream_t)stream);
+        if (st) return st;
+    }
+    return SS_OK;
+}
+
+// ----------------------------------------------------------------------------- host path
+static int check_traj_host(const ss_source& it) {
+    if (it.mode == SS_MOVING_BOUNDS) {
+        const int32_t* b = it.bounds;
+        if (b[0] != 0 || b[it.P - 1] != it.N) return SS_ERR_INVALID;
+        for (int i = 0; i + 1 < it.P; ++i) if (b[i + 1] < b[i]) return SS_ERR_INVALID;
+    } else if (it.mode == SS_MOVING_INDEXED) {
+        for (int n = 0; n < it.N; ++n) { int v = it.idx[n]; if (v < 0 || v + 1 >= it.P) return SS_ERR_INDEX; }
+    }
+    return SS_OK;
+}
+
+static int ensure(char** p, size_t* cap, size_t need) {
+    if (need <= *cap) return SS_OK;
+    CK(cudaDeviceSynchronize());
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    size_t c2 = align_up(need + need / 8, 1 << 20);
+    CK(cudaMalloc((void**)p, c2));
+    *cap = c2;
+    return SS_OK;
+}
+
+extern "C" int ss_render_host(ss_ctx* c, const ss_source* items, int n_items) {
+    if (!c || (!items && n_items > 0) || n_items < 0) return SS_ERR_INVALID;
+    if (n_items == 0) return SS_OK;
+    CK(cudaSetDevice(c->device));
+    for (int i = 0; i < n_items; ++i) {
+        int st = validate_item(items[i]); if (st) return st;
+        st = check_traj_host(items[i]); if (st) return st;
+    }
+    std::vector<int> cuts;
+    make_chunks(c, items, n_items, cuts);
+    std::vector<ss_source> dev(n_items);
+    int rc = SS_OK;
+    for (size_t k = 0; k + 1 < cuts.size() && rc == SS_OK; ++k) {
+        const int first = cuts[k], last = cuts[k + 1];
+        ss_ctx::Slot& sl = c->slot[k & 1];
+        size_t in_b = 0, out_b = 0;
+        for (int i = first; i < last; ++i) {
+            const ss_source& it = items[i];
+            in_b += align_up(sizeof(float) * (size_t)it.N, 256) + align_up(sizeof(float) * (size_t)it.P * it.C * it.L, 256);
+            if (it.mode == SS_MOVING_BOUNDS) in_b += align_up(sizeof(int32_t) * (size_t)it.P, 256);
+            if (it.mode == SS_MOVING_INDEXED) in_b += 2 * align_up(4 * (size_t)it.N, 256);
+            out_b += align_up(sizeof(float) * (size_t)it.C * it.N, 256);
+        }
+        if (k >= 2) CK(cudaEventSynchronize(sl.ev_free));      // slot's previous chunk fully drained
+        if ((rc = ensure(&sl.d_in, &sl.in_cap, in_b)) != SS_OK) break;
+        if ((rc = ensure(&sl.d_out, &sl.out_cap, out_b)) != SS_OK) break;
+        char* pi = sl.d_in; char* po = sl.d_out;
+        for (int i = first; i < last; ++i) {
+            const ss_source& it = items[i];
+            ss_source d = it;
+            size_t nb;
+            nb = sizeof(float) * (size_t)it.N;
+            CK(cudaMemcpyAsync(pi, it.x, nb, cudaMemcpyHostToDevice, c->s_in)); d.x = (const float*)pi; pi += align_up(nb, 256);
+            nb = sizeof(float) * (size_t)it.P * it.C * it.L;
+            CK(cudaMemcpyAsync(pi, it.rir, nb, cudaMemcpyHostToDevice, c->s_in)); d.rir = (const float*)pi; pi += align_up(nb, 256);
+            if (it.mode == SS_MOVING_BOUNDS) {
+                nb = sizeof(int32_t) * (size_t)it.P;
+                CK(cudaMemcpyAsync(pi, it.bounds, nb, cudaMemcpyHostToDevice, c->s_in)); d.bounds = (const int32_t*)pi; pi += align_up(nb, 256);
+            } else if (it.mode == SS_MOVING_INDEXED) {
+                nb = 4 * (size_t)it.N;
+                CK(cudaMemcpyAsync(pi, it.idx, nb, cudaMemcpyHostToDevice, c->s_in)); d.idx = (const int32_t*)pi; pi += align_up(nb, 256);
+                CK(cudaMemcpyAsync(pi, it.w, nb, cudaMemcpyHostToDevice, c->s_in)); d.w = (const float*)pi; pi += align_up(nb, 256);
+            }
+            d.out = (float*)po; po += align_up(sizeof(float) * (size_t)it.C * it.N, 256);
+            dev[i] = d;
+        }
+        CK(cudaEventRecord(sl.ev_in, c->s_in));
+        CK(cudaStreamWaitEvent(c->s_cmp, sl.ev_in, 0));
+        rc = launch_chunk(c, dev.data(), first, last, c->s_cmp);
+        if (rc != SS_OK) break;
+        CK(cudaEventRecord(sl.ev_done, c->s_cmp));
+        CK(cudaStreamWaitEvent(c->s_out, sl.ev_done, 0));
+        for (int i = first; i < last; ++i)
+            CK(cudaMemcpyAsync(items[i].out, dev[i].out, sizeof(float) * (size_t)items[i].C * items[i].N,
+                               cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaEventRecord(sl.ev_free, c->s_out));
+        // the next chunk's H2D into the *other* slot may start now; it must not overtake the
+        // render still reading this slot, which the per-slot ev_free wait above guarantees.
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c->s_in), e2 = cudaStreamSynchronize(c->s_cmp), e3 = cudaStreamSynchronize(c->s_out);
+    if (rc != SS_OK) return rc;
+    CK(e1); CK(e2); CK(e3);
+    return SS_OK;
+}
+
+extern "C" int ss_convolve_fixed_receiver(ss_ctx* c, const float* x, const float* rirs, float* out,
+                                          int32_t N, int32_t C, int32_t L) {
+    ss_source it; memset(&it, 0, sizeof(it));
+    it.x = x; it.rir = rirs; it.out = out; it.N = N; it.P = 1; it.C = C; it.L = L; it.mode = SS_STATIC;
+    return ss_render_host(c, &it, 1);
+}
+extern "C" int ss_convolve_moving_receiver(ss_ctx* c, const float* x, const float* rirs, const int32_t* idx,
+                                           const float* w, float* out, int32_t N, int32_t P, int32_t C, int32_t L) {
+    ss_source it; memset(&it, 0, sizeof(it));
+    it.x = x; it.rir = rirs; it.out = out; it.idx = idx; it.w = w;
+    it.N = N; it.P = P; it.C = C; it.L = L; it.mode = SS_MOVING_INDEXED;
+    return ss_render_host(c, &it, 1);
+}

@@ -1,0 +1,275 @@
+// sonicsim_b200 :: ss_phases.cuh
+//
+// The kernels of the renderer, cut into barrier-free *phases*.  A phase is a function of one
+// thread id, that thread's registers (a struct) and the CTA's shared array.  ss_kernels.cu calls
+// the phases with __syncthreads() between them; tests/emu/ss_emu.cu calls the same phases in a
+// `for (tid)` loop per phase.  All addressing and arithmetic is therefore tested on the CPU.
+#pragma once
+#include "ss_core.cuh"
+
+namespace ss {
+
+// One (utterance, source) unit.  Reference shapes: dry (N,), RIRs (P, C, L), output (C, N)
+// (SonicSim_moving.py:63-96); static source has P = 1 (SonicSim_moving.py:47-61).
+struct Source {
+    const float* x;        // dry waveform, N samples
+    const float* rir;      // (P, C, L) row-major
+    float* out;            // (C, N) row-major, channel-major like torchaudio.save expects
+    const int* bounds;     // compact trajectory: S+1 cumulative segment bounds (mode 1), else null
+    const int* idx;        // per-sample interp_index  (mode 2), else null
+    const float* w;        // per-sample interp_weight (mode 2), else null
+    float2* hspec;         // scratch: P*C*K half spectra of the RIR partitions, pre-scaled by 1/F
+    float2* xspec;         // scratch: nb half spectra of the dry windows
+    float* gain;           // optional per-source linear gain applied at store (null = 1)
+    int N, P, C, L;
+    int K;                 // RIR partitions = ceil(L / kB)
+    int nb;                // output blocks = ceil(N / kB)
+    int mode;              // 0 static, 1 moving (bounds), 2 moving (idx, w)
+    int pad_;
+};
+
+enum { MODE_STATIC = 0, MODE_MOVING_BOUNDS = 1, MODE_MOVING_INDEXED = 2 };
+
+SS_HD int spectra_pairs_h(const Source& s) { return (s.P * s.C * s.K + 1) >> 1; }
+SS_HD int spectra_pairs_x(const Source& s) { return (s.nb + 1) >> 1; }
+SS_HD int render_ctas(const Source& s) {
+    return s.mode == MODE_STATIC ? s.nb * ((s.C + 1) >> 1) : s.nb * s.C;
+}
+
+// largest i with prefix[i] <= v, prefix[0] = 0, prefix has n+1 entries
+SS_HD int find_source(const int* prefix, int n, int v) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (prefix[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// =======================================================================================
+// Spectra kernel: two real rows (a, b) -> one complex FFT -> two stored half spectra.
+// A "row" is 8192 samples  a[n] = (0 <= g0 + n < len && n < ncap) ? base[g0 + n] : 0.
+// =======================================================================================
+struct Row {
+    const float* base;
+    float2* dst;           // null -> row absent (odd count)
+    int g0, len, ncap;
+    float scale;
+};
+
+SS_HD Row make_row_h(const Source& s, int row) {
+    Row r;
+    if (row >= s.P * s.C * s.K) { r.base = nullptr; r.dst = nullptr; r.g0 = 0; r.len = 0; r.ncap = 0; r.scale = 0.f; return r; }
+    int part = row % s.K, pc = row / s.K;
+    r.base = s.rir + (size_t)pc * s.L;
+    r.dst = s.hspec + (size_t)row * kSpec;
+    r.g0 = part * kB; r.len = s.L; r.ncap = kB;
+    r.scale = 1.0f / (float)kF;
+    return r;
+}
+SS_HD Row make_row_x(const Source& s, int blk) {
+    Row r;
+    if (blk >= s.nb) { r.base = nullptr; r.dst = nullptr; r.g0 = 0; r.len = 0; r.ncap = 0; r.scale = 0.f; return r; }
+    r.base = s.x;
+    r.dst = s.xspec + (size_t)blk * kSpec;
+    r.g0 = (blk - 1) * kB; r.len = s.N; r.ncap = kF;
+    r.scale = 1.0f;
+    return r;
+}
+SS_HD float row_at(const Row& r, int n) {
+    int g = r.g0 + n;
+    return (r.dst != nullptr && n < r.ncap && g >= 0 && g < r.len) ? r.base[g] : 0.f;
+}
+
+struct Regs32 { float2 a[16]; float2 b[16]; };
+
+// S1: pass A of the forward transform straight from global memory.
+SS_HD void spectra_phase1(int t, const Row& ra, const Row& rb, float2* s) {
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        int j = t + 256 * h;
+        float2 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = make_float2(row_at(ra, j + 512 * r), row_at(rb, j + 512 * r));
+        fft16<false>(v);
+        passA_store(s, j, v);
+    }
+}
+// generic "load both butterflies t and t+256"
+SS_HD void load2(int t, const float2* s, Regs32& R) { pass_load(s, t, R.a); pass_load(s, t + 256, R.b); }
+
+template <bool INV>
+SS_HD void passB2(int t, float2* s, Regs32& R, const float2* tw) {
+    passB_compute<INV>(t, R.a, tw);       passB_store(s, t, R.a);
+    passB_compute<INV>(t + 256, R.b, tw); passB_store(s, t + 256, R.b);
+}
+
+// S3: pass C + closing radix-2, result (natural order) left in R: a[slot] = Zf[t + 256 r],
+// b[slot] = Zf[4096 + t + 256 r], slot = out16(r).
+SS_HD void spectra_phase3_compute(int t, Regs32& R, const float2* tw) {
+    passC_compute<false>(t, R.a, tw);
+    passC_compute<false>(t + 256, R.b, tw);
+    float2 wt = tw[t];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int sl = out16(r);
+        float2 tmp = cmul(R.b[sl], final_twiddle<false>(t, r, wt));
+        float2 lo = R.a[sl];
+        R.a[sl] = cadd(lo, tmp);
+        R.b[sl] = csub(lo, tmp);
+    }
+}
+SS_HD void spectra_phase3_store(int t, float2* s, const Regs32& R) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        s[pad(t + 256 * r)] = R.a[out16(r)];
+        s[pad(4096 + t + 256 * r)] = R.b[out16(r)];
+    }
+}
+// S4: split Zf into the spectra of a and b (Hermitian parts), scale, store.
+SS_HD void spectra_phase4(int t, const float2* s, const Row& ra, const Row& rb) {
+#pragma unroll 4
+    for (int m = 0; m < 16; ++m) {
+        int k = t + 256 * m;
+        float2 A, Bv;
+        if (k == 0) {
+            float2 z0 = s[pad(0)], zn = s[pad(4096)];
+            A = make_float2(z0.x, zn.x);
+            Bv = make_float2(z0.y, zn.y);
+        } else {
+            float2 zk = s[pad(k)], zm = s[pad(kF - k)];
+            A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+            Bv = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        }
+        if (ra.dst) ra.dst[k] = make_float2(A.x * ra.scale, A.y * ra.scale);
+        if (rb.dst) rb.dst[k] = make_float2(Bv.x * rb.scale, Bv.y * rb.scale);
+    }
+}
+
+// =======================================================================================
+// Render kernel (inverse transform).  One CTA = one output block b of one channel (moving) or
+// one channel pair (static).
+// =======================================================================================
+
+// Z formation fused with pass A.  Hp / Hq: first partition's half spectrum of the two real
+// filters packed into this transform (Hq may be null).  X0 = xspec + b * kSpec; partition `part`
+// pairs with the dry window b - part.
+SS_HD void form_z(int t, const float2* X0, int b, int K, const float2* Hp, const float2* Hq, Regs32& R) {
+    const int jB = passA_jB(t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { R.a[i] = make_float2(0.f, 0.f); R.b[i] = make_float2(0.f, 0.f); }
+    const int kparts = (b + 1 < K) ? b + 1 : K;
+    for (int part = 0; part < kparts; ++part) {
+        const float2* X = X0 - (size_t)part * kSpec;
+        const float2* hp = Hp + (size_t)part * kSpec;
+        const float2* hq = Hq ? Hq + (size_t)part * kSpec : nullptr;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            int kA = t + 512 * m, kB_ = jB + 512 * m;
+            float2 xa = X[kA], xb = X[kB_];
+            cmac(R.a[m], xa, hp[kA]);            // P_A[m]
+            cmac(R.b[m], xb, hp[kB_]);           // P_B[m]
+            if (hq) {
+                cmac(R.b[15 - m], xa, hq[kA]);   // Q_A[m]
+                cmac(R.a[15 - m], xb, hq[kB_]);  // Q_B[m]
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        float2 PA = R.a[m], QA = R.b[15 - m], PB = R.b[m], QB = R.a[15 - m];
+        R.a[m] = z_direct(PA, QA);  R.b[15 - m] = z_mirror(PA, QA);
+        R.b[m] = z_direct(PB, QB);  R.a[15 - m] = z_mirror(PB, QB);
+    }
+    if (t == 0) {
+        // thread 0 owns the self-mirrored butterflies 0 and 256 and the packed (DC, Nyquist) word
+        float pdc = 0.f, pny = 0.f, qdc = 0.f, qny = 0.f;
+        for (int part = 0; part < kparts; ++part) {
+            float2 x0 = (X0 - (size_t)part * kSpec)[0];
+            float2 h0 = (Hp + (size_t)part * kSpec)[0];
+            pdc += x0.x * h0.x; pny += x0.y * h0.y;
+            if (Hq) { float2 g0 = (Hq + (size_t)part * kSpec)[0]; qdc += x0.x * g0.x; qny += x0.y * g0.y; }
+        }
+        float2 tmp[8];
+#pragma unroll
+        for (int r = 8; r < 16; ++r) tmp[r - 8] = R.a[r];
+#pragma unroll
+        for (int r = 9; r < 16; ++r) R.a[r] = R.b[r - 1];
+#pragma unroll
+        for (int r = 8; r < 16; ++r) R.b[r] = tmp[r - 8];
+        R.a[8] = make_float2(pny, qny);
+        R.a[0] = make_float2(pdc, qdc);
+    }
+}
+SS_HD void render_phase1(int t, float2* s, Regs32& R) {
+    fft16<true>(R.a); passA_store(s, passA_jA(t), R.a);
+    fft16<true>(R.b); passA_store(s, passA_jB(t), R.b);
+}
+
+// pass C + closing radix-2 (second half only = the alias-free overlap-save samples), then
+// acc += fa * Re z + fb * Im z with per-sample factors supplied by the functor (called with
+// r = 0..15 in order; it may carry state from one sample to the next).
+template <class Weights>
+SS_HD void render_phase3(int t, Regs32& R, const float2* tw, float (&acc)[16], Weights& wf) {
+    passC_compute<true>(t, R.a, tw);
+    passC_compute<true>(t + 256, R.b, tw);
+    float2 wt = dirw<true>(tw[t]);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int sl = out16(r);
+        float2 z = csub(R.a[sl], cmul(R.b[sl], final_twiddle<true>(t, r, wt)));
+        float fa, fb;
+        wf(r, fa, fb);
+        acc[r] += fa * z.x + fb * z.y;
+    }
+}
+
+// hat functions of positions (p, p+1) at a sample that lies in segment sg with weight w:
+//   reference lerp (SonicSim_moving.py:94):  (1 - w) * conv[sg] + w * conv[sg + 1]
+SS_HD void hat_pair(int sg, float w, int p, float& fa, float& fb) {
+    fa = (sg == p) ? (1.0f - w) : ((sg + 1 == p) ? w : 0.f);
+    fb = (sg == p + 1) ? (1.0f - w) : ((sg == p) ? w : 0.f);
+}
+
+// (seg, w) recomputed per transform instead of being kept in 32 registers across the FFT.
+struct BoundsWeights {      // compact trajectory (MODE_MOVING_BOUNDS)
+    const int* bounds; int S, N, nbase, p, sg;
+    SS_HD BoundsWeights(const Source& s, int n0, int t, int p_) : bounds(s.bounds), S(s.P - 1), N(s.N), nbase(n0 + t), p(p_), sg(-1) {}
+    SS_HD void operator()(int r, float& fa, float& fb) {
+        int n = nbase + 256 * r;
+        if (n >= N) { fa = 0.f; fb = 0.f; return; }
+        if (sg < 0) sg = seg_of(bounds, S, n);
+        else while (sg + 1 < S && bounds[sg + 1] <= n) ++sg;
+        int b0 = bounds[sg], b1 = bounds[sg + 1];
+        hat_pair(sg, seg_weight(n - b0, b1 - b0), p, fa, fb);
+    }
+};
+struct IndexedWeights {     // per-sample arrays (MODE_MOVING_INDEXED)
+    const int* idx; const float* w; int N, nbase, p;
+    SS_HD IndexedWeights(const Source& s, int n0, int t, int p_) : idx(s.idx), w(s.w), N(s.N), nbase(n0 + t), p(p_) {}
+    SS_HD void operator()(int r, float& fa, float& fb) {
+        int n = nbase + 256 * r;
+        if (n >= N) { fa = 0.f; fb = 0.f; return; }
+        hat_pair(idx[n], w[n], p, fa, fb);
+    }
+};
+
+// min / max interp_index over this thread's 16 samples (indexed mode)
+SS_HD void idx_range(int t, int n0, const Source& s, int& pmin, int& pmax) {
+    pmin = 0x7fffffff; pmax = -1;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        int n = n0 + t + 256 * r;
+        if (n < s.N) { int sg = s.idx[n]; pmin = sg < pmin ? sg : pmin; pmax = sg > pmax ? sg : pmax; }
+    }
+}
+
+SS_HD void store_block(int t, int n0, const Source& s, float* out_row, const float (&acc)[16], float g) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        int n = n0 + t + 256 * r;
+        if (n < s.N) out_row[n] = acc[r] * g;
+    }
+}
+
+}  // namespace ss

@@ -1,0 +1,142 @@
+"""Batch-level entry points (additive - NOT reference API).
+
+`convolve_moving` and `render_scene` are the names BASELINE.json's north star uses; the reference
+has no such symbols.  They render many (utterance, source) units with one C-ABI call
+(ss_render_host / ss_render_dev) instead of the reference's serial per-source loop
+(SonicSet.py:77-94).  Host arrays in / out by default; `Renderer.render_device` takes CUDA tensors.
+"""
+import ctypes
+import typing as T
+
+import numpy as np
+
+from . import _lib
+from ._lib import SsSource
+from .SonicSim_moving import _as_f32, _samples_per_interval, bounds_from_counts
+
+
+class MovingSource(T.NamedTuple):
+    """One moving source: dry (N,), RIRs (P, C, L), trajectory as int32 segment bounds (P,)."""
+    dry: T.Any
+    rirs: T.Any
+    bounds: T.Any
+
+
+class StaticSource(T.NamedTuple):
+    """One static source: dry (N,), RIR (C, L)."""
+    dry: T.Any
+    rir: T.Any
+
+
+class Renderer:
+    """Owns the per-device ss_ctx.  One process per GPU (LOCAL_RANK picks the device by default)."""
+
+    def __init__(self, device: T.Optional[int] = None):
+        self.lib = _lib.load()
+        self.device = device
+        self.ctx = _lib.context(device)
+
+    # ------------------------------------------------------------------ host buffers
+    def render_host(self, sources: T.Sequence[T.Union[MovingSource, StaticSource]],
+                    outs: T.Optional[T.Sequence[np.ndarray]] = None) -> T.List[np.ndarray]:
+        """Render every source; returns a list of (C, N) float32 arrays (pinned `outs` may be passed)."""
+        n = len(sources)
+        items = (SsSource * n)()
+        keep = []
+        results = []
+        for i, s in enumerate(sources):
+            x = _as_f32(s.dry).reshape(-1)
+            if isinstance(s, StaticSource):
+                h = _as_f32(s.rir)
+                C, L = h.shape
+                P, mode, bounds = 1, _lib.SS_STATIC, None
+            else:
+                h = _as_f32(s.rirs)
+                P, C, L = h.shape
+                bounds = np.ascontiguousarray(s.bounds, dtype=np.int32)
+                mode = _lib.SS_MOVING_BOUNDS
+                if bounds.shape != (P,):
+                    raise ValueError("bounds must have P entries (cumulative segment bounds with leading 0)")
+            N = x.shape[0]
+            out = outs[i] if outs is not None else np.empty((C, N), dtype=np.float32)
+            if out.shape != (C, N) or out.dtype != np.float32 or not out.flags.c_contiguous:
+                raise ValueError("out[%d] must be C-contiguous float32 of shape (C, N)" % i)
+            items[i] = SsSource(x=x.ctypes.data, rir=h.ctypes.data, out=out.ctypes.data,
+                                bounds=bounds.ctypes.data if bounds is not None else None,
+                                N=N, P=P, C=C, L=L, mode=mode)
+            keep.append((x, h, bounds, out))
+            results.append(out)
+        _lib.check(self.lib.ss_render_host(self.ctx, items, n))
+        return results
+
+    # ------------------------------------------------------------------ device tensors
+    def render_device(self, sources, outs, stream: T.Optional[int] = None):
+        """`sources`: MovingSource / StaticSource whose fields are CUDA float32 / int32 tensors;
+        `outs`: preallocated CUDA (C, N) tensors.  Asynchronous on `stream` (torch current stream)."""
+        import torch
+        n = len(sources)
+        items = (SsSource * n)()
+        for i, s in enumerate(sources):
+            if isinstance(s, StaticSource):
+                C, L = s.rir.shape
+                items[i] = SsSource(x=s.dry.data_ptr(), rir=s.rir.data_ptr(), out=outs[i].data_ptr(),
+                                    N=s.dry.numel(), P=1, C=C, L=L, mode=_lib.SS_STATIC)
+            else:
+                P, C, L = s.rirs.shape
+                items[i] = SsSource(x=s.dry.data_ptr(), rir=s.rirs.data_ptr(), out=outs[i].data_ptr(),
+                                    bounds=s.bounds.data_ptr(), N=s.dry.numel(), P=P, C=C, L=L,
+                                    mode=_lib.SS_MOVING_BOUNDS)
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.lib.ss_render_dev(self.ctx, items, n, ctypes.c_void_p(stream)))
+
+    def launch_count(self) -> int:
+        return int(self.lib.ss_launch_count(self.ctx))
+
+    def reset_stats(self):
+        self.lib.ss_reset_stats(self.ctx)
+
+    def set_profiling(self, on: bool):
+        _lib.check(self.lib.ss_set_profiling(self.ctx, 1 if on else 0))
+
+    def get_profile(self):
+        """(ms in k_spectra, ms in k_render, launch pairs) since the previous call."""
+        a, b, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        _lib.check(self.lib.ss_get_profile(self.ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)))
+        return a.value, b.value, n.value
+
+    def set_chunk_bytes(self, nbytes: int):
+        _lib.check(self.lib.ss_set_chunk_bytes(self.ctx, int(nbytes)))
+
+
+_default: T.Optional[Renderer] = None
+
+
+def default_renderer() -> Renderer:
+    global _default
+    if _default is None:
+        _default = Renderer()
+    return _default
+
+
+def trajectory_bounds(receiver_position, total_samples: int) -> np.ndarray:
+    """Positions (P, 3) -> int32 segment bounds (P,), via the reference's constant-speed rule
+    (SonicSim_moving.py:32-39; consumes the global NumPy RNG like the reference)."""
+    return bounds_from_counts(_samples_per_interval(np.asarray(receiver_position), total_samples))
+
+
+def convolve_moving(dry_list, rirs_list, positions_list) -> T.List[np.ndarray]:
+    """Batched interpolate_moving_audio: for each i, dry (N,), RIRs (P, C, L), positions (P, 3)."""
+    srcs = [MovingSource(d, r, trajectory_bounds(p, np.asarray(d).shape[-1]))
+            for d, r, p in zip(dry_list, rirs_list, positions_list)]
+    return default_renderer().render_host(srcs)
+
+
+def render_scene(moving: T.Sequence[T.Tuple], static: T.Sequence[T.Tuple] = ()) -> T.Tuple[T.List[np.ndarray], T.List[np.ndarray]]:
+    """One scene of SonicSet.process_single (SonicSet.py:77-94) in a single call:
+    `moving` = [(dry (N,), rirs (P, C, L), positions (P, 3)), ...], `static` = [(dry (N,), rir (C, L)), ...].
+    Returns (moving stems, static stems), each (C, N) float32."""
+    srcs: T.List = [MovingSource(d, r, trajectory_bounds(p, np.asarray(d).shape[-1])) for d, r, p in moving]
+    srcs += [StaticSource(d, r) for d, r in static]
+    outs = default_renderer().render_host(srcs)
+    return outs[: len(moving)], outs[len(moving):]

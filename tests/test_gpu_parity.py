@@ -1,0 +1,163 @@
+"""Parity of the CUDA path (through the C ABI / drop-in functions) with the oracle and the
+reference's golden vectors.  Tolerance: relative RMS <= 1e-4 per output tensor (BASELINE north star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TOL
+from oracle import sonicsim_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sm():
+    from sonicsim_b200 import SonicSim_moving
+    return SonicSim_moving
+
+
+def bounds_of(idx, P):
+    return np.concatenate([[0], np.cumsum(np.bincount(idx, minlength=P - 1))]).astype(np.int32)
+
+
+def test_native_library_is_the_code_that_runs(sm):
+    sm.convolve_fixed_receiver(np.ones((1, 64), np.float32), np.ones((1, 4), np.float32))
+    maps = open("/proc/self/maps").read()
+    assert "libsonicsim_b200.so" in maps
+
+
+def test_golden_fixed(sm, golden):
+    g = golden("convolve_fixed_receiver")
+    for k in range(int(g["n_cases"])):
+        y = sm.convolve_fixed_receiver(g[f"x{k}"], g[f"h{k}"])
+        assert isinstance(y, np.ndarray) and y.dtype == np.float32 and y.shape == g[f"y{k}"].shape
+        assert so.rel_rms(y, g[f"y{k}"]) < TOL
+        y_t = sm.convolve_fixed_receiver(torch.from_numpy(g[f"x{k}"]), torch.from_numpy(g[f"h{k}"]))   # SonicSet.py:93
+        assert np.array_equal(y, y_t)
+
+
+def test_golden_moving(sm, golden):
+    g = golden("convolve_moving_receiver")
+    for k in range(int(g["n_cases"])):
+        y = sm.convolve_moving_receiver(g[f"x{k}"], g[f"h{k}"], g[f"idx{k}"].astype(np.int64), g[f"w{k}"])
+        assert y.dtype == np.float32 and y.shape == g[f"y{k}"].shape
+        assert so.rel_rms(y, g[f"y{k}"]) < TOL
+
+
+def test_golden_interpolate_moving_audio(sm, golden):
+    g = golden("interpolate_moving_audio")
+    for k in range(int(g["n_cases"])):
+        np.random.seed(int(g[f"seed{k}"]))
+        y = sm.interpolate_moving_audio(torch.from_numpy(g[f"x{k}"]), torch.from_numpy(g[f"h{k}"]),
+                                        [list(p) for p in g[f"pos{k}"]])
+        assert isinstance(y, torch.Tensor) and y.dtype == torch.float32 and not y.is_cuda
+        assert so.rel_rms(y.numpy(), g[f"y{k}"]) < TOL
+        # list-of-tensors form of ir1_list (SonicSim_moving.py:122 np.array(list))
+        np.random.seed(int(g[f"seed{k}"]))
+        y2 = sm.interpolate_moving_audio(torch.from_numpy(g[f"x{k}"]), [torch.from_numpy(t) for t in g[f"h{k}"]],
+                                         g[f"pos{k}"])
+        assert np.array_equal(y.numpy(), y2.numpy())
+
+
+@pytest.mark.parametrize("P,C,L,N", [(3, 1, 1, 100), (2, 2, 4096, 4096), (2, 1, 4097, 8193), (9, 3, 600, 12289),
+                                     (5, 2, 9000, 5000), (40, 6, 4096, 100000), (13, 5, 257, 70001)])
+def test_shapes_and_partitions(sm, P, C, L, N):
+    rng = np.random.default_rng(P * 1000 + L)
+    x, h, pos = so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L), so.synth_path(rng, P)
+    np.random.seed(7)
+    idx, w = so.setup_dynamic_interp(pos, N)
+    ref = so.convolve_moving_receiver(x, h, idx, w)
+    assert so.rel_rms(sm.convolve_moving_receiver(x, h, idx, w), ref) < TOL
+
+
+def test_empty_segments_ragged_and_random_indices(sm):
+    rng = np.random.default_rng(3)
+    P, C, L, N = 9, 2, 40, 5
+    x, pos = so.synth_dry(rng, N), so.synth_path(rng, P)
+    h = rng.standard_normal((P, C, L)).astype(np.float32)
+    pos[3] = pos[2]
+    for seed in range(50):
+        np.random.seed(seed)
+        try:
+            idx, w = so.setup_dynamic_interp(pos, N)
+            break
+        except ValueError:
+            continue
+    assert so.rel_rms(sm.convolve_moving_receiver(x, h, idx, w), so.convolve_moving_receiver(x, h, idx, w)) < TOL
+    # arbitrary (non-monotone) index / weight arrays
+    P, C, L, N = 7, 2, 300, 9000
+    x, h = so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L)
+    idx = rng.integers(0, P - 1, N)
+    w = rng.random(N).astype(np.float32)
+    assert so.rel_rms(sm.convolve_moving_receiver(x, h, idx, w), so.convolve_moving_receiver(x, h, idx, w)) < TOL
+    with pytest.raises(IndexError):
+        sm.convolve_moving_receiver(x, h, np.full(N, P - 1), w)
+
+
+def test_batch_api_matches_single_calls_and_device_path(sm):
+    from sonicsim_b200 import render
+    rng = np.random.default_rng(11)
+    moving, static = [], []
+    for i in range(5):
+        N = 20000 + 3000 * i
+        P = 4 + i
+        moving.append((so.synth_dry(rng, N), so.synth_rirs(rng, P, 3, 700 + 100 * i), so.synth_path(rng, P)))
+    for i in range(3):
+        static.append((so.synth_dry(rng, 15000), so.synth_rirs(rng, 1, 2 + i, 512)[0]))
+    np.random.seed(5)
+    ym, ys = render.render_scene(moving, static)
+    np.random.seed(5)
+    for (x, h, pos), y in zip(moving, ym):
+        idx, w = so.setup_dynamic_interp(pos, x.shape[0])
+        assert so.rel_rms(y, so.convolve_moving_receiver(x, h, idx, w)) < TOL
+    for (x, h), y in zip(static, ys):
+        assert so.rel_rms(y, so.convolve_fixed_receiver(x[None], h)) < TOL
+    # device-resident path gives bit-identical results to the host path
+    R = render.default_renderer()
+    np.random.seed(5)
+    srcs, outs = [], []
+    for (x, h, pos) in moving:
+        b = render.trajectory_bounds(pos, x.shape[0])
+        srcs.append(render.MovingSource(torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda(), torch.from_numpy(b).cuda()))
+        outs.append(torch.empty((h.shape[1], x.shape[0]), device="cuda"))
+    R.render_device(srcs, outs)
+    torch.cuda.synchronize()
+    for y, o in zip(ym, outs):
+        assert np.array_equal(y, o.cpu().numpy())
+
+
+def test_full_size_cfg2_against_oracle_and_properties(sm):
+    """BASELINE configs[1] shape: C=6, P=40, L=4096, N=480000 (one speaker)."""
+    rng = np.random.default_rng(2000)
+    P, C, L, N = 40, 6, 4096, 480000
+    x, h, pos = so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L), so.synth_path(rng, P)
+    np.random.seed(2000)
+    idx, w = so.setup_dynamic_interp(pos, N)
+    y = sm.convolve_moving_receiver(x, h, idx, w)
+    ref = so.convolve_moving_receiver(x, h, idx, w)
+    assert so.rel_rms(y, ref) < TOL
+    # compact-trajectory path (interpolate_moving_audio) is bit-identical to the (idx, w) path
+    np.random.seed(2000)
+    y2 = sm.interpolate_moving_audio(torch.from_numpy(x[None]), torch.from_numpy(h[:, None]), pos).numpy()
+    assert np.array_equal(y, y2)
+    # linearity in the RIR set
+    h2 = so.synth_rirs(rng, P, C, L)
+    ya = sm.convolve_moving_receiver(x, h2, idx, w)
+    yab = sm.convolve_moving_receiver(x, (h + 0.5 * h2).astype(np.float32), idx, w)
+    assert so.rel_rms(yab, y + 0.5 * ya) < 1e-5
+    # delta RIR -> identity; boundary continuity of the interpolation
+    hd = np.zeros((P, C, L), np.float32)
+    hd[:, :, 0] = 1.0
+    yd = sm.convolve_moving_receiver(x, hd, idx, w)
+    assert so.rel_rms(yd, np.broadcast_to(x, (C, N))) < 2e-6
+
+
+def test_long_rir_partitioned_cfg4_shape_reduced(sm):
+    """configs[3] flavour: L = 32768 (8 partitions), 4 channels; N reduced so the oracle runs in seconds."""
+    rng = np.random.default_rng(4000)
+    P, C, L, N = 12, 4, 32768, 200000
+    x, h, pos = so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L, sr=48000, t60=1.5), so.synth_path(rng, P)
+    np.random.seed(4000)
+    idx, w = so.setup_dynamic_interp(pos, N)
+    assert so.rel_rms(sm.convolve_moving_receiver(x, h, idx, w), so.convolve_moving_receiver(x, h, idx, w)) < TOL
+    assert so.rel_rms(sm.convolve_fixed_receiver(x[None], h[0]), so.convolve_fixed_receiver(x[None], h[0])) < TOL
