@@ -162,6 +162,8 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     U, K, W = args.utterances, args.steps, args.warmup
     R = render.Renderer(local_rank)
+    if args.chunk_mb:
+        R.set_chunk_bytes(args.chunk_mb << 20)
     items = make_inputs(U, rank)
     n_src = len(items)
     C, N = CFG["C"], CFG["N"]
@@ -299,6 +301,7 @@ def main():
     ap.add_argument("--utterances", type=int, default=16, help="utterances per GPU per step")
     ap.add_argument("--cpu-reps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk-mb", type=int, default=0, help="override the library's L2-sized spectra budget")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -136,10 +136,11 @@ def test_full_size_cfg2_against_oracle_and_properties(sm):
     y = sm.convolve_moving_receiver(x, h, idx, w)
     ref = so.convolve_moving_receiver(x, h, idx, w)
     assert so.rel_rms(y, ref) < TOL
-    # compact-trajectory path (interpolate_moving_audio) is bit-identical to the (idx, w) path
+    # compact-trajectory path (interpolate_moving_audio): same weights computed on the device
     np.random.seed(2000)
     y2 = sm.interpolate_moving_audio(torch.from_numpy(x[None]), torch.from_numpy(h[:, None]), pos).numpy()
-    assert np.array_equal(y, y2)
+    print("idx-vs-bounds path: rel-RMS %.3g, max abs diff %.3g" % (so.rel_rms(y2, y), np.abs(y2 - y).max()))
+    assert so.rel_rms(y2, y) < 1e-6
     # linearity in the RIR set
     h2 = so.synth_rirs(rng, P, C, L)
     ya = sm.convolve_moving_receiver(x, h2, idx, w)
