@@ -41,6 +41,33 @@ template <bool INV> SS_HD float2 rot90(float2 a) { return INV ? make_float2(-a.y
 // conjugate the twiddle for the inverse transform
 template <bool INV> SS_HD float2 dirw(float2 w) { return INV ? make_float2(w.x, -w.y) : w; }
 
+// Streaming 8-byte load: spectra are read once per CTA, keep them out of L1 so the twiddle tables
+// stay resident there.
+SS_HD float2 ldg_stream(const float2* p) {
+#if defined(__CUDA_ARCH__)
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+#else
+    return *p;
+#endif
+}
+SS_HD float2 ldg_cached(const float2* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// Twiddle tables (forward sign, filled in double precision on the host):
+//   tw [m]           = exp(-2 pi i m / 8192)            m < 8192   (closing radix-2)
+//   twB[r * 16 + k]  = exp(-2 pi i k r / 256)           r, k < 16  (pass B)
+//   twC[r * 256 + k] = exp(-2 pi i k r / 4096)          r < 16, k < 256 (pass C)
+// r-major so that a warp (consecutive k) reads consecutive words.
+struct Tables { const float2* tw; const float2* twB; const float2* twC; };
+constexpr int kTabB = 16 * 16, kTabC = 16 * 256;
+
 template <bool INV>
 SS_HD void fft4(float2& v0, float2& v1, float2& v2, float2& v3) {
     float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3), a3 = rot90<INV>(csub(v1, v3));
@@ -70,16 +97,11 @@ SS_HD void fft16(float2 (&v)[16]) {
 // register slot that holds output index r after fft16
 SS_HD constexpr int out16(int r) { return 4 * (r & 3) + (r >> 2); }
 
-// v[r] *= w^r, r = 1..15, powers built with a depth-4 product tree.
-SS_HD void twiddle16(float2 (&v)[16], float2 w1) {
-    float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
-    float2 w5 = cmul(w4, w1), w6 = cmul(w3, w3), w7 = cmul(w4, w3), w8 = cmul(w4, w4);
-    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
-    v[5] = cmul(v[5], w5); v[6] = cmul(v[6], w6); v[7] = cmul(v[7], w7); v[8] = cmul(v[8], w8);
-    v[9]  = cmul(v[9],  cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2));
-    v[11] = cmul(v[11], cmul(w8, w3)); v[12] = cmul(v[12], cmul(w8, w4));
-    v[13] = cmul(v[13], cmul(w8, w5)); v[14] = cmul(v[14], cmul(w8, w6));
-    v[15] = cmul(v[15], cmul(w8, w7));
+// v[r] *= tab[r * stride], r = 1..15 (tab points at the entry of this butterfly's k)
+template <bool INV, int STRIDE>
+SS_HD void twiddle16(float2 (&v)[16], const float2* tab) {
+#pragma unroll
+    for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], dirw<INV>(ldg_cached(tab + r * STRIDE)));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -90,36 +112,39 @@ SS_HD void twiddle16(float2 (&v)[16], float2 w1) {
 // ---------------------------------------------------------------------------------------
 
 // Pass A (Ns = 1) store: v holds fft16 outputs of butterfly j (no input twiddles when Ns = 1).
+// pad(16 j + r) = 17 j + r.
 SS_HD void passA_store(float2* s, int j, const float2 (&v)[16]) {
+    float2* d = s + 17 * j;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s[pad(16 * j + r)] = v[out16(r)];
+    for (int r = 0; r < 16; ++r) d[r] = v[out16(r)];
 }
 
+// pad(j + 512 r) = pad(j) + 544 r
 SS_HD void pass_load(const float2* s, int j, float2 (&v)[16]) {
+    const float2* p = s + pad(j);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = s[pad(j + 512 * r)];
+    for (int r = 0; r < 16; ++r) v[r] = p[544 * r];
 }
 
 // Pass B (Ns = 16): twiddle exp(-+2 pi i k r / 256), k = j % 16
 template <bool INV>
-SS_HD void passB_compute(int j, float2 (&v)[16], const float2* tw) {
-    int k = j & 15;
-    twiddle16(v, dirw<INV>(tw[k * 32]));
+SS_HD void passB_compute(int j, float2 (&v)[16], const Tables& T) {
+    twiddle16<INV, 16>(v, T.twB + (j & 15));
     fft16<INV>(v);
 }
+// destination (j / 16) * 256 + (j % 16) + 16 r, padded = (j / 16) * 272 + (j % 16) + 17 r
 SS_HD void passB_store(float2* s, int j, const float2 (&v)[16]) {
-    int base = (j >> 4) * 256 + (j & 15);
+    float2* d = s + (j >> 4) * 272 + (j & 15);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s[pad(base + 16 * r)] = v[out16(r)];
+    for (int r = 0; r < 16; ++r) d[17 * r] = v[out16(r)];
 }
 
 // Pass C (Ns = 256): twiddle exp(-+2 pi i k r / 4096), k = j % 256.  Outputs stay in registers:
 // butterfly j (< 256) yields natural-order points j + 256 r of the first half-length transform,
 // butterfly j + 256 the same points of the second one.
 template <bool INV>
-SS_HD void passC_compute(int j, float2 (&v)[16], const float2* tw) {
-    int k = j & 255;
-    twiddle16(v, dirw<INV>(tw[k * 2]));
+SS_HD void passC_compute(int j, float2 (&v)[16], const Tables& T) {
+    twiddle16<INV, 256>(v, T.twC + (j & 255));
     fft16<INV>(v);
 }
 

@@ -25,12 +25,16 @@
 
 using namespace ss;
 
-__device__ float2 g_tw[kF];          // exp(-2 pi i m / 8192), filled from the host in double precision
+// twiddle tables, filled from the host in double precision (ss_create)
+__device__ float2 g_tw[kF];          // exp(-2 pi i m / 8192)
+__device__ float2 g_twB[kTabB];      // [r][k] exp(-2 pi i k r / 256)
+__device__ float2 g_twC[kTabC];      // [r][k] exp(-2 pi i k r / 4096)
 
 // ----------------------------------------------------------------------------- k_spectra
 __global__ void __launch_bounds__(kThreads, 2)
 k_spectra(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_src) {
     extern __shared__ float2 smem[];
+    const Tables T{g_tw, g_twB, g_twC};
     const int t = threadIdx.x;
     const int si = find_source(prefix, n_src, blockIdx.x);
     const Source& S = srcs[si];
@@ -45,10 +49,10 @@ k_spectra(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n
     __syncthreads();
     load2(t, smem, R);
     __syncthreads();
-    passB2<false>(t, smem, R, g_tw);
+    passB2<false>(t, smem, R, T);
     __syncthreads();
     load2(t, smem, R);
-    spectra_phase3_compute(t, R, g_tw);
+    spectra_phase3_compute(t, R, T);
     __syncthreads();
     spectra_phase3_store(t, smem, R);
     __syncthreads();
@@ -60,60 +64,29 @@ __global__ void __launch_bounds__(kThreads, 2)
 k_render(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_src) {
     extern __shared__ float2 smem[];
     __shared__ int s_red[2 * (kThreads / 32)];
+    const Tables T{g_tw, g_twB, g_twC};
     const int t = threadIdx.x;
     const int si = find_source(prefix, n_src, blockIdx.x);
     const Source& S = srcs[si];
     const int local = blockIdx.x - prefix[si];
-    const float g = S.gain ? *S.gain : 1.0f;
-    Regs32 R;
+    const int mode = S.mode;
 
-    if (S.mode == MODE_STATIC) {
+    // decode the work item: block b, output row(s), range of transforms
+    int b, c, p_lo, p_hi, sg0 = 0;
+    if (mode == MODE_STATIC) {
         const int ncp = (S.C + 1) >> 1;
-        const int b = local / ncp, cp = local - b * ncp;
-        const int c0 = 2 * cp, c1 = c0 + 1;
-        const int n0 = b * kB;
-        const float2* X0 = S.xspec + (size_t)b * kSpec;
-        const float2* Hp = S.hspec + (size_t)c0 * S.K * kSpec;
-        const float2* Hq = (c1 < S.C) ? S.hspec + (size_t)c1 * S.K * kSpec : nullptr;
-        form_z(t, X0, b, S.K, Hp, Hq, R);
-        render_phase1(t, smem, R);
-        __syncthreads();
-        load2(t, smem, R);
-        __syncthreads();
-        passB2<true>(t, smem, R, g_tw);
-        __syncthreads();
-        load2(t, smem, R);
-        // static: Re -> channel c0, Im -> channel c1
-        passC_compute<true>(t, R.a, g_tw);
-        passC_compute<true>(t + 256, R.b, g_tw);
-        const float2 wt = dirw<true>(g_tw[t]);
-        float* o0 = S.out + (size_t)c0 * S.N;
-        float* o1 = S.out + (size_t)(c1 < S.C ? c1 : c0) * S.N;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int sl = out16(r);
-            float2 z = csub(R.a[sl], cmul(R.b[sl], final_twiddle<true>(t, r, wt)));
-            int n = n0 + t + 256 * r;
-            if (n < S.N) {
-                o0[n] = z.x * g;
-                if (c1 < S.C) o1[n] = z.y * g;
-            }
-        }
-        return;
+        b = local / ncp; c = 2 * (local - b * ncp);
+        p_lo = 0; p_hi = 0;
+    } else {
+        b = local / S.C; c = local - b * S.C;
     }
-
-    // moving source: one channel per CTA
-    const int b = local / S.C, c = local - b * S.C;
     const int n0 = b * kB;
-    float acc[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) acc[r] = 0.f;
-    int p_lo, p_hi;
-    if (S.mode == MODE_MOVING_BOUNDS) {
+    if (mode == MODE_MOVING_BOUNDS) {
         const int n_last = (n0 + kB < S.N ? n0 + kB : S.N) - 1;
         p_lo = seg_of(S.bounds, S.P - 1, n0);
         p_hi = seg_of(S.bounds, S.P - 1, n_last) + 1;
-    } else {
+        sg0 = seg_of(S.bounds, S.P - 1, n0 + t < S.N ? n0 + t : S.N - 1);
+    } else if (mode == MODE_MOVING_INDEXED) {
         int pmin, pmax;
         idx_range(t, n0, S, pmin, pmax);
 #pragma unroll
@@ -131,22 +104,31 @@ k_render(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_
         p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
     }
     const float2* X0 = S.xspec + (size_t)b * kSpec;
+    float* row = S.out + (size_t)c * S.N;
+    Regs32 R;
     for (int p = p_lo; p <= p_hi; p += 2) {
-        const float2* Hp = S.hspec + ((size_t)p * S.C + c) * S.K * kSpec;
-        const float2* Hq = (p + 1 <= p_hi) ? S.hspec + ((size_t)(p + 1) * S.C + c) * S.K * kSpec : nullptr;
+        const float2 *Hp, *Hq;
+        if (mode == MODE_STATIC) {
+            Hp = S.hspec + (size_t)c * S.K * kSpec;
+            Hq = (c + 1 < S.C) ? Hp + (size_t)S.K * kSpec : nullptr;
+        } else {
+            Hp = S.hspec + ((size_t)p * S.C + c) * S.K * kSpec;
+            Hq = (p + 1 <= p_hi) ? Hp + (size_t)S.C * S.K * kSpec : nullptr;
+        }
         form_z(t, X0, b, S.K, Hp, Hq, R);
+        if (p != p_lo) __syncthreads();          // previous transform's pass-C loads are done
         render_phase1(t, smem, R);
         __syncthreads();
         load2(t, smem, R);
         __syncthreads();
-        passB2<true>(t, smem, R, g_tw);
+        passB2<true>(t, smem, R, T);
         __syncthreads();
         load2(t, smem, R);
-        __syncthreads();          // next iteration's pass A overwrites smem
-        if (S.mode == MODE_MOVING_BOUNDS) { BoundsWeights wf(S, n0, t, p); render_phase3(t, R, g_tw, acc, wf); }
-        else { IndexedWeights wf(S, n0, t, p); render_phase3(t, R, g_tw, acc, wf); }
+        render_phase3(t, R, T);
+        if (mode == MODE_MOVING_BOUNDS) { MovingSinkBounds sk(S, row, n0, t, p, sg0, p == p_lo); render_epilogue(R, sk); }
+        else if (mode == MODE_MOVING_INDEXED) { MovingSinkIndexed sk(S, row, n0, t, p, p == p_lo); render_epilogue(R, sk); }
+        else { StaticSink sk{row, (c + 1 < S.C) ? row + S.N : nullptr, S.N, n0 + t}; render_epilogue(R, sk); }
     }
-    store_block(t, n0, S, S.out + (size_t)c * S.N, acc, g);
 }
 
 // ============================================================================= host side
@@ -208,6 +190,19 @@ extern "C" int ss_create(int device, ss_ctx** out) {
         tw[m] = make_float2((float)cos(a), (float)sin(a));
     }
     CK(cudaMemcpyToSymbol(g_tw, tw.data(), sizeof(float2) * kF));
+    std::vector<float2> tb(kTabB), tc(kTabC);
+    for (int r = 0; r < 16; ++r) {
+        for (int k = 0; k < 16; ++k) {
+            double a = -2.0 * M_PI * (double)(k * r) / 256.0;
+            tb[r * 16 + k] = make_float2((float)cos(a), (float)sin(a));
+        }
+        for (int k = 0; k < 256; ++k) {
+            double a = -2.0 * M_PI * (double)(k * r) / 4096.0;
+            tc[r * 256 + k] = make_float2((float)cos(a), (float)sin(a));
+        }
+    }
+    CK(cudaMemcpyToSymbol(g_twB, tb.data(), sizeof(float2) * kTabB));
+    CK(cudaMemcpyToSymbol(g_twC, tc.data(), sizeof(float2) * kTabC));
     const int smem = kPadF * (int)sizeof(float2);
     CK(cudaFuncSetAttribute(k_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -341,7 +336,6 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
         s.bounds = it.mode == SS_MOVING_BOUNDS ? it.bounds : nullptr;
         s.idx = it.mode == SS_MOVING_INDEXED ? it.idx : nullptr;
         s.w = it.mode == SS_MOVING_INDEXED ? it.w : nullptr;
-        s.gain = nullptr;
         s.N = it.N; s.P = it.P; s.C = it.C; s.L = it.L;
         s.K = (it.L + kB - 1) / kB; s.nb = (it.N + kB - 1) / kB;
         s.mode = it.mode;

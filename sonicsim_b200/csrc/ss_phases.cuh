@@ -20,12 +20,11 @@ struct Source {
     const float* w;        // per-sample interp_weight (mode 2), else null
     float2* hspec;         // scratch: P*C*K half spectra of the RIR partitions, pre-scaled by 1/F
     float2* xspec;         // scratch: nb half spectra of the dry windows
-    float* gain;           // optional per-source linear gain applied at store (null = 1)
     int N, P, C, L;
     int K;                 // RIR partitions = ceil(L / kB)
     int nb;                // output blocks = ceil(N / kB)
     int mode;              // 0 static, 1 moving (bounds), 2 moving (idx, w)
-    int pad_;
+    int pad_[3];
 };
 
 enum { MODE_STATIC = 0, MODE_MOVING_BOUNDS = 1, MODE_MOVING_INDEXED = 2 };
@@ -95,21 +94,25 @@ SS_HD void spectra_phase1(int t, const Row& ra, const Row& rb, float2* s) {
         passA_store(s, j, v);
     }
 }
-// generic "load both butterflies t and t+256"
-SS_HD void load2(int t, const float2* s, Regs32& R) { pass_load(s, t, R.a); pass_load(s, t + 256, R.b); }
+// generic "load both butterflies t and t+256":  pad(t + 256) = pad(t) + 272
+SS_HD void load2(int t, const float2* s, Regs32& R) {
+    const float2* p = s + pad(t);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { R.a[r] = p[544 * r]; R.b[r] = p[544 * r + 272]; }
+}
 
 template <bool INV>
-SS_HD void passB2(int t, float2* s, Regs32& R, const float2* tw) {
-    passB_compute<INV>(t, R.a, tw);       passB_store(s, t, R.a);
-    passB_compute<INV>(t + 256, R.b, tw); passB_store(s, t + 256, R.b);
+SS_HD void passB2(int t, float2* s, Regs32& R, const Tables& T) {
+    passB_compute<INV>(t, R.a, T);       passB_store(s, t, R.a);
+    passB_compute<INV>(t + 256, R.b, T); passB_store(s, t + 256, R.b);
 }
 
 // S3: pass C + closing radix-2, result (natural order) left in R: a[slot] = Zf[t + 256 r],
 // b[slot] = Zf[4096 + t + 256 r], slot = out16(r).
-SS_HD void spectra_phase3_compute(int t, Regs32& R, const float2* tw) {
-    passC_compute<false>(t, R.a, tw);
-    passC_compute<false>(t + 256, R.b, tw);
-    float2 wt = tw[t];
+SS_HD void spectra_phase3_compute(int t, Regs32& R, const Tables& T) {
+    passC_compute<false>(t, R.a, T);
+    passC_compute<false>(t + 256, R.b, T);
+    float2 wt = ldg_cached(T.tw + t);
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         const int sl = out16(r);
@@ -119,11 +122,13 @@ SS_HD void spectra_phase3_compute(int t, Regs32& R, const float2* tw) {
         R.b[sl] = csub(lo, tmp);
     }
 }
+// natural order to shared: pad(t + 256 r) = pad(t) + 272 r, pad(4096 + i) = 4352 + pad(i)
 SS_HD void spectra_phase3_store(int t, float2* s, const Regs32& R) {
+    float2* d = s + pad(t);
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-        s[pad(t + 256 * r)] = R.a[out16(r)];
-        s[pad(4096 + t + 256 * r)] = R.b[out16(r)];
+        d[272 * r] = R.a[out16(r)];
+        d[272 * r + 4352] = R.b[out16(r)];
     }
 }
 // S4: split Zf into the spectra of a and b (Hermitian parts), scale, store.
@@ -160,18 +165,27 @@ SS_HD void form_z(int t, const float2* X0, int b, int K, const float2* Hp, const
     for (int i = 0; i < 16; ++i) { R.a[i] = make_float2(0.f, 0.f); R.b[i] = make_float2(0.f, 0.f); }
     const int kparts = (b + 1 < K) ? b + 1 : K;
     for (int part = 0; part < kparts; ++part) {
-        const float2* X = X0 - (size_t)part * kSpec;
-        const float2* hp = Hp + (size_t)part * kSpec;
-        const float2* hq = Hq ? Hq + (size_t)part * kSpec : nullptr;
+        const float2* xa_p = X0 - (size_t)part * kSpec + t;
+        const float2* xb_p = X0 - (size_t)part * kSpec + jB;
+        const float2* ha_p = Hp + (size_t)part * kSpec + t;
+        const float2* hb_p = Hp + (size_t)part * kSpec + jB;
+        if (Hq) {
+            const float2* ga_p = Hq + (size_t)part * kSpec + t;
+            const float2* gb_p = Hq + (size_t)part * kSpec + jB;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            int kA = t + 512 * m, kB_ = jB + 512 * m;
-            float2 xa = X[kA], xb = X[kB_];
-            cmac(R.a[m], xa, hp[kA]);            // P_A[m]
-            cmac(R.b[m], xb, hp[kB_]);           // P_B[m]
-            if (hq) {
-                cmac(R.b[15 - m], xa, hq[kA]);   // Q_A[m]
-                cmac(R.a[15 - m], xb, hq[kB_]);  // Q_B[m]
+            for (int m = 0; m < 8; ++m) {
+                float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
+                cmac(R.a[m], xa, ldg_stream(ha_p + 512 * m));            // P_A[m]
+                cmac(R.b[m], xb, ldg_stream(hb_p + 512 * m));            // P_B[m]
+                cmac(R.b[15 - m], xa, ldg_stream(ga_p + 512 * m));       // Q_A[m]
+                cmac(R.a[15 - m], xb, ldg_stream(gb_p + 512 * m));       // Q_B[m]
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
+                cmac(R.a[m], xa, ldg_stream(ha_p + 512 * m));
+                cmac(R.b[m], xb, ldg_stream(hb_p + 512 * m));
             }
         }
     }
@@ -206,22 +220,23 @@ SS_HD void render_phase1(int t, float2* s, Regs32& R) {
     fft16<true>(R.b); passA_store(s, passA_jB(t), R.b);
 }
 
-// pass C + closing radix-2 (second half only = the alias-free overlap-save samples), then
-// acc += fa * Re z + fb * Im z with per-sample factors supplied by the functor (called with
-// r = 0..15 in order; it may carry state from one sample to the next).
-template <class Weights>
-SS_HD void render_phase3(int t, Regs32& R, const float2* tw, float (&acc)[16], Weights& wf) {
-    passC_compute<true>(t, R.a, tw);
-    passC_compute<true>(t + 256, R.b, tw);
-    float2 wt = dirw<true>(tw[t]);
+// pass C + closing radix-2 (second half only = the alias-free overlap-save samples):
+// leaves z[4096 + t + 256 r] in R.a[out16(r)].
+SS_HD void render_phase3(int t, Regs32& R, const Tables& T) {
+    passC_compute<true>(t, R.a, T);
+    passC_compute<true>(t + 256, R.b, T);
+    float2 wt = dirw<true>(ldg_cached(T.tw + t));
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         const int sl = out16(r);
-        float2 z = csub(R.a[sl], cmul(R.b[sl], final_twiddle<true>(t, r, wt)));
-        float fa, fb;
-        wf(r, fa, fb);
-        acc[r] += fa * z.x + fb * z.y;
+        R.a[sl] = csub(R.a[sl], cmul(R.b[sl], final_twiddle<true>(t, r, wt)));
     }
+}
+// epilogue: the sink is called with r = 0..15 in order; it may carry state from sample to sample
+template <class Sink>
+SS_HD void render_epilogue(const Regs32& R, Sink& sink) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sink(r, R.a[out16(r)]);
 }
 
 // hat functions of positions (p, p+1) at a sample that lies in segment sg with weight w:
@@ -231,26 +246,52 @@ SS_HD void hat_pair(int sg, float w, int p, float& fa, float& fb) {
     fb = (sg == p + 1) ? (1.0f - w) : ((sg == p) ? w : 0.f);
 }
 
-// (seg, w) recomputed per transform instead of being kept in 32 registers across the FFT.
-struct BoundsWeights {      // compact trajectory (MODE_MOVING_BOUNDS)
-    const int* bounds; int S, N, nbase, p, sg;
-    SS_HD BoundsWeights(const Source& s, int n0, int t, int p_) : bounds(s.bounds), S(s.P - 1), N(s.N), nbase(n0 + t), p(p_), sg(-1) {}
-    SS_HD void operator()(int r, float& fa, float& fb) {
+// Output row of one CTA.  `first` = this is the first transform of the block (plain store),
+// otherwise the partial result already in `row` is read back and added to (only blocks that
+// straddle a waypoint need a second transform), which keeps 16 accumulators out of the register
+// file during the FFT passes.
+struct MovingSinkBounds {       // compact trajectory (MODE_MOVING_BOUNDS)
+    const int* bounds; float* row; int S, N, nbase, p, sg, b0, b1; double step; bool first;
+    SS_HD MovingSinkBounds(const Source& s, float* row_, int n0, int t, int p_, int sg0, bool first_)
+        : bounds(s.bounds), row(row_), S(s.P - 1), N(s.N), nbase(n0 + t), p(p_), sg(sg0), first(first_) {
+        b0 = bounds[sg]; b1 = bounds[sg + 1]; step = 1.0 / (double)(b1 - b0);
+    }
+    SS_HD void operator()(int r, float2 z) {
         int n = nbase + 256 * r;
-        if (n >= N) { fa = 0.f; fb = 0.f; return; }
-        if (sg < 0) sg = seg_of(bounds, S, n);
-        else while (sg + 1 < S && bounds[sg + 1] <= n) ++sg;
-        int b0 = bounds[sg], b1 = bounds[sg + 1];
-        hat_pair(sg, seg_weight(n - b0, b1 - b0), p, fa, fb);
+        if (n >= N) return;
+        if (n >= b1) {
+            do { ++sg; b1 = bounds[sg + 1]; } while (n >= b1);
+            b0 = bounds[sg]; step = 1.0 / (double)(b1 - b0);
+        }
+        float w = (float)((double)(n - b0) * step);      // == np.linspace(0, 1, num, False)[i] as float32
+        float fa, fb;
+        hat_pair(sg, w, p, fa, fb);
+        float v = fa * z.x + fb * z.y;
+        if (!first) v += row[n];
+        row[n] = v;
     }
 };
-struct IndexedWeights {     // per-sample arrays (MODE_MOVING_INDEXED)
-    const int* idx; const float* w; int N, nbase, p;
-    SS_HD IndexedWeights(const Source& s, int n0, int t, int p_) : idx(s.idx), w(s.w), N(s.N), nbase(n0 + t), p(p_) {}
-    SS_HD void operator()(int r, float& fa, float& fb) {
+struct MovingSinkIndexed {      // per-sample arrays (MODE_MOVING_INDEXED)
+    const int* idx; const float* w; float* row; int N, nbase, p; bool first;
+    SS_HD MovingSinkIndexed(const Source& s, float* row_, int n0, int t, int p_, bool first_)
+        : idx(s.idx), w(s.w), row(row_), N(s.N), nbase(n0 + t), p(p_), first(first_) {}
+    SS_HD void operator()(int r, float2 z) {
         int n = nbase + 256 * r;
-        if (n >= N) { fa = 0.f; fb = 0.f; return; }
+        if (n >= N) return;
+        float fa, fb;
         hat_pair(idx[n], w[n], p, fa, fb);
+        float v = fa * z.x + fb * z.y;
+        if (!first) v += row[n];
+        row[n] = v;
+    }
+};
+struct StaticSink {             // Re -> channel c0, Im -> channel c1 (row1 null if C is odd)
+    float* row0; float* row1; int N, nbase;
+    SS_HD void operator()(int r, float2 z) {
+        int n = nbase + 256 * r;
+        if (n >= N) return;
+        row0[n] = z.x;
+        if (row1) row1[n] = z.y;
     }
 };
 
@@ -261,14 +302,6 @@ SS_HD void idx_range(int t, int n0, const Source& s, int& pmin, int& pmax) {
     for (int r = 0; r < 16; ++r) {
         int n = n0 + t + 256 * r;
         if (n < s.N) { int sg = s.idx[n]; pmin = sg < pmin ? sg : pmin; pmax = sg > pmax ? sg : pmax; }
-    }
-}
-
-SS_HD void store_block(int t, int n0, const Source& s, float* out_row, const float (&acc)[16], float g) {
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        int n = n0 + t + 256 * r;
-        if (n < s.N) out_row[n] = acc[r] * g;
     }
 }
 

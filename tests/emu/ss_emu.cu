@@ -14,16 +14,30 @@
 
 using namespace ss;
 
-static std::vector<float2> make_tw() {
-    std::vector<float2> tw(kF);
-    for (int m = 0; m < kF; ++m) {
-        double a = -2.0 * M_PI * (double)m / (double)kF;
-        tw[m] = make_float2((float)cos(a), (float)sin(a));
+struct HostTables {
+    std::vector<float2> tw, tb, tc;
+    Tables T;
+    HostTables() : tw(kF), tb(kTabB), tc(kTabC) {
+        for (int m = 0; m < kF; ++m) {
+            double a = -2.0 * M_PI * (double)m / (double)kF;
+            tw[m] = make_float2((float)cos(a), (float)sin(a));
+        }
+        for (int r = 0; r < 16; ++r) {
+            for (int k = 0; k < 16; ++k) {
+                double a = -2.0 * M_PI * (double)(k * r) / 256.0;
+                tb[r * 16 + k] = make_float2((float)cos(a), (float)sin(a));
+            }
+            for (int k = 0; k < 256; ++k) {
+                double a = -2.0 * M_PI * (double)(k * r) / 4096.0;
+                tc[r * 256 + k] = make_float2((float)cos(a), (float)sin(a));
+            }
+        }
+        T.tw = tw.data(); T.twB = tb.data(); T.twC = tc.data();
     }
-    return tw;
-}
+};
+static const Tables& tables() { static HostTables h; return h.T; }
 
-static void cta_spectra(const Source& S, int local, const float2* tw) {
+static void cta_spectra(const Source& S, int local, const Tables& T) {
     std::vector<float2> smem(kPadF);
     std::vector<Regs32> R(kThreads);
     Row ra, rb;
@@ -33,58 +47,32 @@ static void cta_spectra(const Source& S, int local, const float2* tw) {
     float2* s = smem.data();
     for (int t = 0; t < kThreads; ++t) spectra_phase1(t, ra, rb, s);
     for (int t = 0; t < kThreads; ++t) load2(t, s, R[t]);
-    for (int t = 0; t < kThreads; ++t) passB2<false>(t, s, R[t], tw);
-    for (int t = 0; t < kThreads; ++t) { load2(t, s, R[t]); spectra_phase3_compute(t, R[t], tw); }
+    for (int t = 0; t < kThreads; ++t) passB2<false>(t, s, R[t], T);
+    for (int t = 0; t < kThreads; ++t) { load2(t, s, R[t]); spectra_phase3_compute(t, R[t], T); }
     for (int t = 0; t < kThreads; ++t) spectra_phase3_store(t, s, R[t]);
     for (int t = 0; t < kThreads; ++t) spectra_phase4(t, s, ra, rb);
 }
 
-static void ifft_passes(float2* s, std::vector<Regs32>& R, const float2* tw) {
-    for (int t = 0; t < kThreads; ++t) render_phase1(t, s, R[t]);
-    for (int t = 0; t < kThreads; ++t) load2(t, s, R[t]);
-    for (int t = 0; t < kThreads; ++t) passB2<true>(t, s, R[t], tw);
-    for (int t = 0; t < kThreads; ++t) load2(t, s, R[t]);
-}
-
-static void cta_render(const Source& S, int local, const float2* tw) {
+static void cta_render(const Source& S, int local, const Tables& T) {
     std::vector<float2> smem(kPadF);
     std::vector<Regs32> R(kThreads);
     float2* s = smem.data();
-    if (S.mode == MODE_STATIC) {
+    const int mode = S.mode;
+    int b, c, p_lo = 0, p_hi = 0;
+    std::vector<int> sg0(kThreads, 0);
+    if (mode == MODE_STATIC) {
         const int ncp = (S.C + 1) >> 1;
-        const int b = local / ncp, cp = local - b * ncp;
-        const int c0 = 2 * cp, c1 = c0 + 1;
-        const int n0 = b * kB;
-        const float2* X0 = S.xspec + (size_t)b * kSpec;
-        const float2* Hp = S.hspec + (size_t)c0 * S.K * kSpec;
-        const float2* Hq = (c1 < S.C) ? S.hspec + (size_t)c1 * S.K * kSpec : nullptr;
-        for (int t = 0; t < kThreads; ++t) form_z(t, X0, b, S.K, Hp, Hq, R[t]);
-        ifft_passes(s, R, tw);
-        for (int t = 0; t < kThreads; ++t) {
-            passC_compute<true>(t, R[t].a, tw);
-            passC_compute<true>(t + 256, R[t].b, tw);
-            const float2 wt = dirw<true>(tw[t]);
-            for (int r = 0; r < 16; ++r) {
-                const int sl = out16(r);
-                float2 z = csub(R[t].a[sl], cmul(R[t].b[sl], final_twiddle<true>(t, r, wt)));
-                int n = n0 + t + 256 * r;
-                if (n < S.N) {
-                    S.out[(size_t)c0 * S.N + n] = z.x;
-                    if (c1 < S.C) S.out[(size_t)c1 * S.N + n] = z.y;
-                }
-            }
-        }
-        return;
+        b = local / ncp; c = 2 * (local - b * ncp);
+    } else {
+        b = local / S.C; c = local - b * S.C;
     }
-    const int b = local / S.C, c = local - b * S.C;
     const int n0 = b * kB;
-    std::vector<float> accs(kThreads * 16, 0.f);
-    int p_lo, p_hi;
-    if (S.mode == MODE_MOVING_BOUNDS) {
+    if (mode == MODE_MOVING_BOUNDS) {
         const int n_last = (n0 + kB < S.N ? n0 + kB : S.N) - 1;
         p_lo = seg_of(S.bounds, S.P - 1, n0);
         p_hi = seg_of(S.bounds, S.P - 1, n_last) + 1;
-    } else {
+        for (int t = 0; t < kThreads; ++t) sg0[t] = seg_of(S.bounds, S.P - 1, n0 + t < S.N ? n0 + t : S.N - 1);
+    } else if (mode == MODE_MOVING_INDEXED) {
         int pmin = 0x7fffffff, pmax = -1;
         for (int t = 0; t < kThreads; ++t) {
             int a, bb;
@@ -95,20 +83,27 @@ static void cta_render(const Source& S, int local, const float2* tw) {
         p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
     }
     const float2* X0 = S.xspec + (size_t)b * kSpec;
+    float* row = S.out + (size_t)c * S.N;
     for (int p = p_lo; p <= p_hi; p += 2) {
-        const float2* Hp = S.hspec + ((size_t)p * S.C + c) * S.K * kSpec;
-        const float2* Hq = (p + 1 <= p_hi) ? S.hspec + ((size_t)(p + 1) * S.C + c) * S.K * kSpec : nullptr;
-        for (int t = 0; t < kThreads; ++t) form_z(t, X0, b, S.K, Hp, Hq, R[t]);
-        ifft_passes(s, R, tw);
-        for (int t = 0; t < kThreads; ++t) {
-            float (&acc)[16] = *reinterpret_cast<float (*)[16]>(&accs[t * 16]);
-            if (S.mode == MODE_MOVING_BOUNDS) { BoundsWeights wf(S, n0, t, p); render_phase3(t, R[t], tw, acc, wf); }
-            else { IndexedWeights wf(S, n0, t, p); render_phase3(t, R[t], tw, acc, wf); }
+        const float2 *Hp, *Hq;
+        if (mode == MODE_STATIC) {
+            Hp = S.hspec + (size_t)c * S.K * kSpec;
+            Hq = (c + 1 < S.C) ? Hp + (size_t)S.K * kSpec : nullptr;
+        } else {
+            Hp = S.hspec + ((size_t)p * S.C + c) * S.K * kSpec;
+            Hq = (p + 1 <= p_hi) ? Hp + (size_t)S.C * S.K * kSpec : nullptr;
         }
-    }
-    for (int t = 0; t < kThreads; ++t) {
-        float (&acc)[16] = *reinterpret_cast<float (*)[16]>(&accs[t * 16]);
-        store_block(t, n0, S, S.out + (size_t)c * S.N, acc, 1.0f);
+        for (int t = 0; t < kThreads; ++t) form_z(t, X0, b, S.K, Hp, Hq, R[t]);
+        for (int t = 0; t < kThreads; ++t) render_phase1(t, s, R[t]);
+        for (int t = 0; t < kThreads; ++t) load2(t, s, R[t]);
+        for (int t = 0; t < kThreads; ++t) passB2<true>(t, s, R[t], T);
+        for (int t = 0; t < kThreads; ++t) {
+            load2(t, s, R[t]);
+            render_phase3(t, R[t], T);
+            if (mode == MODE_MOVING_BOUNDS) { MovingSinkBounds sk(S, row, n0, t, p, sg0[t], p == p_lo); render_epilogue(R[t], sk); }
+            else if (mode == MODE_MOVING_INDEXED) { MovingSinkIndexed sk(S, row, n0, t, p, p == p_lo); render_epilogue(R[t], sk); }
+            else { StaticSink sk{row, (c + 1 < S.C) ? row + S.N : nullptr, S.N, n0 + t}; render_epilogue(R[t], sk); }
+        }
     }
 }
 
@@ -117,7 +112,7 @@ extern "C" {
 // Emulate k_spectra + k_render for one source.  mode: 0 static, 1 bounds, 2 (idx, w).
 int emu_render(const float* x, const float* rir, float* out, const int32_t* bounds, const int32_t* idx,
                const float* w, int N, int P, int C, int L, int mode) {
-    static std::vector<float2> tw = make_tw();
+    const Tables& T = tables();
     Source S;
     memset(&S, 0, sizeof(S));
     S.x = x; S.rir = rir; S.out = out; S.bounds = bounds; S.idx = idx; S.w = w;
@@ -125,22 +120,22 @@ int emu_render(const float* x, const float* rir, float* out, const int32_t* boun
     std::vector<float2> hs((size_t)P * C * S.K * kSpec), xs((size_t)S.nb * kSpec);
     S.hspec = hs.data(); S.xspec = xs.data();
     const int ns = spectra_pairs_h(S) + spectra_pairs_x(S);
-    for (int i = 0; i < ns; ++i) cta_spectra(S, i, tw.data());
+    for (int i = 0; i < ns; ++i) cta_spectra(S, i, T);
     const int nr = render_ctas(S);
-    for (int i = 0; i < nr; ++i) cta_render(S, i, tw.data());
+    for (int i = 0; i < nr; ++i) cta_render(S, i, T);
     return 0;
 }
 
 // forward 8192-point FFT of z = a + i b via the spectra kernel phases; returns the two half spectra
 int emu_spectra_pair(const float* a, const float* b, int len, float* specA, float* specB) {
-    static std::vector<float2> tw = make_tw();
+    const Tables& T = tables();
     Source S; memset(&S, 0, sizeof(S));
     std::vector<float> rir(2 * (size_t)len);
     memcpy(rir.data(), a, sizeof(float) * len); memcpy(rir.data() + len, b, sizeof(float) * len);
     S.rir = rir.data(); S.P = 1; S.C = 2; S.L = len; S.K = (len + kB - 1) / kB; S.N = 1; S.nb = 1;
     std::vector<float2> hs((size_t)2 * S.K * kSpec);
     S.hspec = hs.data();
-    for (int i = 0; i < spectra_pairs_h(S); ++i) cta_spectra(S, i, tw.data());
+    for (int i = 0; i < spectra_pairs_h(S); ++i) cta_spectra(S, i, T);
     // return partition 0 of each row
     memcpy(specA, hs.data(), sizeof(float2) * kSpec);
     memcpy(specB, hs.data() + (size_t)S.K * kSpec, sizeof(float2) * kSpec);
