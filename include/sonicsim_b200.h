@@ -87,6 +87,49 @@ int ss_convolve_moving_receiver(ss_ctx* ctx, const float* source_audio, const fl
                                 const int32_t* interp_index, const float* interp_weight, float* out,
                                 int32_t N, int32_t P, int32_t C, int32_t L);            /* :63-96 */
 
+/* ---- loudness: SonicSim_audio.lufs_norm (SonicSim_audio.py:68-81) = pyloudnorm 0.1.1
+ * Meter(rate, block_size).integrated_loudness + normalize.loudness.  The gating-block sample
+ * bounds are computed by the caller exactly as pyloudnorm does (Python float expressions
+ * truncated with int()), and passed as `brk` = the sorted distinct bounds (n_e + 1 values) plus,
+ * per gating block j, the range [blk_lo[j], blk_hi[j]) of elementary intervals it covers. */
+typedef struct {
+    const float* data;        /* element (n, c) at data[n * stride_n + c * stride_c]                   */
+    float* out;               /* N*C contiguous floats = gain * data (may alias data); NULL = measure  */
+    const int32_t* brk;       /* n_e + 1                                                               */
+    const int32_t* blk_lo;    /* n_blocks                                                              */
+    const int32_t* blk_hi;    /* n_blocks                                                              */
+    double* scratch;          /* C * n_e doubles                                                       */
+    double* result;           /* 2 doubles: integrated loudness (LUFS, may be -inf), linear gain       */
+    int64_t stride_n, stride_c;
+    int32_t N, C, n_e, n_blocks;
+    double rate;              /* sample rate                                                           */
+    double block_size;        /* T_g in seconds (0.4, or N / rate for short clips, SonicSim_audio.py:69) */
+    double target_lufs;       /* `norm` of lufs_norm                                                   */
+} ss_loud_item;
+
+/* Device pointers, asynchronous on `stream`; all items share one sample rate. */
+int ss_loudness_dev(ss_ctx* ctx, const ss_loud_item* items, int n_items, void* stream);
+
+/* One stem in host memory (any layout through the strides); returns when `out` (if given), the
+ * measured loudness and the linear gain are available. */
+int ss_lufs_norm_host(ss_ctx* ctx, const float* data, float* out, int32_t N, int32_t C,
+                      int64_t stride_n, int64_t stride_c, double rate, double block_size,
+                      double target_lufs, const int32_t* brk, int32_t n_e, const int32_t* blk_lo,
+                      const int32_t* blk_hi, int32_t n_blocks, double* loudness, double* gain);
+
+/* Optional per-source post-processing of ss_render_host_ex: measure the rendered (C, N) stem and
+ * normalise it to `target_lufs` on the device before it is copied out (SonicSet.py:97-101 applies
+ * get_lufs_norm_audio to every stem right after rendering it).  brk == NULL skips the source. */
+typedef struct {
+    const int32_t* brk; const int32_t* blk_lo; const int32_t* blk_hi;   /* host arrays, see ss_loud_item */
+    int32_t n_e, n_blocks;
+    double rate, block_size, target_lufs;
+    double* result;           /* host, 2 doubles: measured LUFS, linear gain (may be NULL)             */
+} ss_post_lufs;
+
+/* ss_render_host + optional loudness normalisation of each stem while it is still in HBM. */
+int ss_render_host_ex(ss_ctx* ctx, const ss_source* items, int n_items, const ss_post_lufs* post);
+
 /* Counters since ss_create / ss_reset_stats: kernels launched and device time is NOT measured
  * here (bench.py uses CUDA events); this is the launch count bench.py reports as gpu_launches. */
 int64_t ss_launch_count(const ss_ctx* ctx);

@@ -12,13 +12,29 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libsonicsim_b200.so")
-SOURCES = ["ss_kernels.cu"]
-HEADERS = ["ss_core.cuh", "ss_phases.cuh", os.path.join("..", "..", "include", "sonicsim_b200.h")]
+SOURCES = ["ss_kernels.cu", "ss_loudness.cu"]
+HEADERS = ["ss_core.cuh", "ss_phases.cuh", "ss_loud.cuh", "ss_internal.h", os.path.join("..", "..", "include", "sonicsim_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
 SS_OK, SS_ERR_INVALID, SS_ERR_INDEX, SS_ERR_CUDA, SS_ERR_NOMEM, SS_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 SS_STATIC, SS_MOVING_BOUNDS, SS_MOVING_INDEXED = 0, 1, 2
+
+
+class SsLoudItem(ctypes.Structure):
+    """`ss_loud_item` of include/sonicsim_b200.h."""
+    _fields_ = [("data", ctypes.c_void_p), ("out", ctypes.c_void_p), ("brk", ctypes.c_void_p),
+                ("blk_lo", ctypes.c_void_p), ("blk_hi", ctypes.c_void_p), ("scratch", ctypes.c_void_p),
+                ("result", ctypes.c_void_p), ("stride_n", ctypes.c_int64), ("stride_c", ctypes.c_int64),
+                ("N", ctypes.c_int32), ("C", ctypes.c_int32), ("n_e", ctypes.c_int32), ("n_blocks", ctypes.c_int32),
+                ("rate", ctypes.c_double), ("block_size", ctypes.c_double), ("target_lufs", ctypes.c_double)]
+
+
+class SsPostLufs(ctypes.Structure):
+    """`ss_post_lufs` of include/sonicsim_b200.h."""
+    _fields_ = [("brk", ctypes.c_void_p), ("blk_lo", ctypes.c_void_p), ("blk_hi", ctypes.c_void_p),
+                ("n_e", ctypes.c_int32), ("n_blocks", ctypes.c_int32), ("rate", ctypes.c_double),
+                ("block_size", ctypes.c_double), ("target_lufs", ctypes.c_double), ("result", ctypes.c_void_p)]
 
 
 class SsSource(ctypes.Structure):
@@ -84,8 +100,13 @@ def load():
         lib.ss_set_chunk_bytes.argtypes = [vp, i64]
         lib.ss_render_dev.argtypes = [vp, ctypes.POINTER(SsSource), ctypes.c_int, vp]
         lib.ss_render_host.argtypes = [vp, ctypes.POINTER(SsSource), ctypes.c_int]
+        lib.ss_render_host_ex.argtypes = [vp, ctypes.POINTER(SsSource), ctypes.c_int, ctypes.POINTER(SsPostLufs)]
         lib.ss_convolve_fixed_receiver.argtypes = [vp, vp, vp, vp, i32, i32, i32]
         lib.ss_convolve_moving_receiver.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32]
+        dbl = ctypes.c_double
+        lib.ss_loudness_dev.argtypes = [vp, ctypes.POINTER(SsLoudItem), ctypes.c_int, vp]
+        lib.ss_lufs_norm_host.argtypes = [vp, vp, vp, i32, i32, i64, i64, dbl, dbl, dbl, vp, i32, vp, vp, i32,
+                                          ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
         lib.ss_launch_count.argtypes = [vp]
         lib.ss_launch_count.restype = i64
         lib.ss_reset_stats.argtypes = [vp]
@@ -101,8 +122,8 @@ def load():
 
 
 EXPORTS = ["ss_version", "ss_strerror", "ss_last_cuda_error", "ss_create", "ss_destroy",
-           "ss_set_chunk_bytes", "ss_render_dev", "ss_render_host", "ss_convolve_fixed_receiver",
-           "ss_convolve_moving_receiver", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
+           "ss_set_chunk_bytes", "ss_render_dev", "ss_render_host", "ss_render_host_ex", "ss_convolve_fixed_receiver",
+           "ss_convolve_moving_receiver", "ss_loudness_dev", "ss_lufs_norm_host", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
            "ss_host_free"]
 
 

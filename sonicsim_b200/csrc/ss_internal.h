@@ -1,0 +1,38 @@
+// sonicsim_b200 :: ss_internal.h - host-side state shared by the translation units of the library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+
+#include "../../include/sonicsim_b200.h"
+
+struct ss_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int64_t chunk_bytes = 48ll << 20;
+    // scratch for spectra
+    char* d_scratch = nullptr; size_t scratch_cap = 0;
+    // descriptor ring (pinned host + device)
+    static const int kRing = 4;
+    char* h_desc[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    char* d_desc[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    size_t desc_cap[kRing] = {0, 0, 0, 0};
+    cudaEvent_t desc_ev[kRing];
+    int ring_pos = 0;
+    // host path
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    struct Slot { char* d_in = nullptr; size_t in_cap = 0; char* d_out = nullptr; size_t out_cap = 0;
+                  cudaEvent_t ev_in, ev_done, ev_free; } slot[2];
+    int64_t launches = 0;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool profiling = false;
+    struct Prof { cudaEvent_t e0, e1, e2; };
+    std::vector<Prof> prof;
+};
+
+extern thread_local int g_last_cuda;
+#define CK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_last_cuda = (int)e_; \
+    return e_ == cudaErrorMemoryAllocation ? SS_ERR_NOMEM : SS_ERR_CUDA; } } while (0)
+
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -20,7 +20,7 @@
 #include <string.h>
 #include <vector>
 
-#include "../../include/sonicsim_b200.h"
+#include "ss_internal.h"
 #include "ss_phases.cuh"
 
 using namespace ss;
@@ -82,10 +82,17 @@ k_render(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_
     }
     const int n0 = b * kB;
     if (mode == MODE_MOVING_BOUNDS) {
-        const int n_last = (n0 + kB < S.N ? n0 + kB : S.N) - 1;
-        p_lo = seg_of(S.bounds, S.P - 1, n0);
-        p_hi = seg_of(S.bounds, S.P - 1, n_last) + 1;
-        sg0 = seg_of(S.bounds, S.P - 1, n0 + t < S.N ? n0 + t : S.N - 1);
+        // two lanes search the block's first / last segment, everyone else walks from there
+        if (t < 2) {
+            const int n_last = (n0 + kB < S.N ? n0 + kB : S.N) - 1;
+            s_red[t] = seg_of(S.bounds, S.P - 1, t == 0 ? n0 : n_last);
+        }
+        __syncthreads();
+        p_lo = s_red[0];
+        p_hi = s_red[1] + 1;
+        const int nn = n0 + t < S.N ? n0 + t : S.N - 1;
+        sg0 = p_lo;
+        while (S.bounds[sg0 + 1] <= nn) ++sg0;
     } else if (mode == MODE_MOVING_INDEXED) {
         int pmin, pmax;
         idx_range(t, n0, S, pmin, pmax);
@@ -132,33 +139,7 @@ k_render(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_
 }
 
 // ============================================================================= host side
-struct ss_ctx {
-    int device = 0;
-    int sm_count = 148;
-    int64_t chunk_bytes = 48ll << 20;
-    // scratch for spectra
-    char* d_scratch = nullptr; size_t scratch_cap = 0;
-    // descriptor ring (pinned host + device)
-    static const int kRing = 4;
-    char* h_desc[kRing] = {nullptr, nullptr, nullptr, nullptr};
-    char* d_desc[kRing] = {nullptr, nullptr, nullptr, nullptr};
-    size_t desc_cap[kRing] = {0, 0, 0, 0};
-    cudaEvent_t desc_ev[kRing];
-    int ring_pos = 0;
-    // host path
-    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
-    struct Slot { char* d_in = nullptr; size_t in_cap = 0; char* d_out = nullptr; size_t out_cap = 0;
-                  cudaEvent_t ev_in, ev_done, ev_free; } slot[2];
-    int64_t launches = 0;
-    // optional per-kernel timing (CUDA events on the launching stream)
-    bool profiling = false;
-    struct Prof { cudaEvent_t e0, e1, e2; };
-    std::vector<Prof> prof;
-};
-
-static thread_local int g_last_cuda = 0;
-#define CK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_last_cuda = (int)e_; \
-    return e_ == cudaErrorMemoryAllocation ? SS_ERR_NOMEM : SS_ERR_CUDA; } } while (0)
+thread_local int g_last_cuda = 0;
 
 extern "C" int ss_version(void) { return 100; }
 extern "C" int ss_last_cuda_error(void) { return g_last_cuda; }
@@ -174,7 +155,6 @@ extern "C" const char* ss_strerror(int st) {
     }
 }
 
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 extern "C" int ss_create(int device, ss_ctx** out) {
     if (!out) return SS_ERR_INVALID;
@@ -417,17 +397,27 @@ static int ensure(char** p, size_t* cap, size_t need) {
     return SS_OK;
 }
 
-extern "C" int ss_render_host(ss_ctx* c, const ss_source* items, int n_items) {
+extern "C" int ss_loudness_dev(ss_ctx* c, const ss_loud_item* items, int n_items, void* stream);
+
+// Host path: H2D -> k_spectra -> k_render [-> loudness measure + in-place gain] -> D2H, pipelined
+// over chunks on three streams with two device slots.
+extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items, const ss_post_lufs* post) {
     if (!c || (!items && n_items > 0) || n_items < 0) return SS_ERR_INVALID;
     if (n_items == 0) return SS_OK;
     CK(cudaSetDevice(c->device));
     for (int i = 0; i < n_items; ++i) {
         int st = validate_item(items[i]); if (st) return st;
         st = check_traj_host(items[i]); if (st) return st;
+        if (post && post[i].brk) {
+            if (!post[i].blk_lo || !post[i].blk_hi || post[i].n_e <= 0 || post[i].rate <= 0 || items[i].C > 8) return SS_ERR_INVALID;
+            if (post[i].rate != post[0].rate && post[0].brk) return SS_ERR_INVALID;
+        }
     }
     std::vector<int> cuts;
     make_chunks(c, items, n_items, cuts);
     std::vector<ss_source> dev(n_items);
+    std::vector<ss_loud_item> loud;
+    std::vector<double*> res_dev(n_items, nullptr);
     int rc = SS_OK;
     for (size_t k = 0; k + 1 < cuts.size() && rc == SS_OK; ++k) {
         const int first = cuts[k], last = cuts[k + 1];
@@ -439,11 +429,16 @@ extern "C" int ss_render_host(ss_ctx* c, const ss_source* items, int n_items) {
             if (it.mode == SS_MOVING_BOUNDS) in_b += align_up(sizeof(int32_t) * (size_t)it.P, 256);
             if (it.mode == SS_MOVING_INDEXED) in_b += 2 * align_up(4 * (size_t)it.N, 256);
             out_b += align_up(sizeof(float) * (size_t)it.C * it.N, 256);
+            if (post && post[i].brk) {
+                in_b += align_up(4 * (size_t)(post[i].n_e + 1), 256) + 2 * align_up(4 * (size_t)(post[i].n_blocks + 1), 256);
+                out_b += align_up(8 * (size_t)it.C * post[i].n_e, 256) + 256;
+            }
         }
         if (k >= 2) CK(cudaEventSynchronize(sl.ev_free));      // slot's previous chunk fully drained
         if ((rc = ensure(&sl.d_in, &sl.in_cap, in_b)) != SS_OK) break;
         if ((rc = ensure(&sl.d_out, &sl.out_cap, out_b)) != SS_OK) break;
         char* pi = sl.d_in; char* po = sl.d_out;
+        loud.clear();
         for (int i = first; i < last; ++i) {
             const ss_source& it = items[i];
             ss_source d = it;
@@ -462,16 +457,41 @@ extern "C" int ss_render_host(ss_ctx* c, const ss_source* items, int n_items) {
             }
             d.out = (float*)po; po += align_up(sizeof(float) * (size_t)it.C * it.N, 256);
             dev[i] = d;
+            if (post && post[i].brk) {
+                const ss_post_lufs& pl = post[i];
+                ss_loud_item li; memset(&li, 0, sizeof(li));
+                nb = 4 * (size_t)(pl.n_e + 1);
+                CK(cudaMemcpyAsync(pi, pl.brk, nb, cudaMemcpyHostToDevice, c->s_in)); li.brk = (const int32_t*)pi; pi += align_up(nb, 256);
+                nb = 4 * (size_t)pl.n_blocks;
+                if (nb) CK(cudaMemcpyAsync(pi, pl.blk_lo, nb, cudaMemcpyHostToDevice, c->s_in));
+                li.blk_lo = (const int32_t*)pi; pi += align_up(nb + 4, 256);
+                if (nb) CK(cudaMemcpyAsync(pi, pl.blk_hi, nb, cudaMemcpyHostToDevice, c->s_in));
+                li.blk_hi = (const int32_t*)pi; pi += align_up(nb + 4, 256);
+                li.scratch = (double*)po; po += align_up(8 * (size_t)it.C * pl.n_e, 256);
+                li.result = (double*)po; po += 256;
+                res_dev[i] = li.result;
+                li.data = d.out; li.out = d.out;                 // (C, N) stem, normalised in place
+                li.stride_n = 1; li.stride_c = it.N; li.N = it.N; li.C = it.C; li.n_e = pl.n_e; li.n_blocks = pl.n_blocks;
+                li.rate = pl.rate; li.block_size = pl.block_size; li.target_lufs = pl.target_lufs;
+                loud.push_back(li);
+            }
         }
         CK(cudaEventRecord(sl.ev_in, c->s_in));
         CK(cudaStreamWaitEvent(c->s_cmp, sl.ev_in, 0));
         rc = launch_chunk(c, dev.data(), first, last, c->s_cmp);
         if (rc != SS_OK) break;
+        if (!loud.empty()) {
+            rc = ss_loudness_dev(c, loud.data(), (int)loud.size(), (void*)c->s_cmp);
+            if (rc != SS_OK) break;
+        }
         CK(cudaEventRecord(sl.ev_done, c->s_cmp));
         CK(cudaStreamWaitEvent(c->s_out, sl.ev_done, 0));
-        for (int i = first; i < last; ++i)
+        for (int i = first; i < last; ++i) {
             CK(cudaMemcpyAsync(items[i].out, dev[i].out, sizeof(float) * (size_t)items[i].C * items[i].N,
                                cudaMemcpyDeviceToHost, c->s_out));
+            if (res_dev[i] && post[i].result)
+                CK(cudaMemcpyAsync(post[i].result, res_dev[i], 2 * sizeof(double), cudaMemcpyDeviceToHost, c->s_out));
+        }
         CK(cudaEventRecord(sl.ev_free, c->s_out));
         // the next chunk's H2D into the *other* slot may start now; it must not overtake the
         // render still reading this slot, which the per-slot ev_free wait above guarantees.
@@ -480,6 +500,10 @@ extern "C" int ss_render_host(ss_ctx* c, const ss_source* items, int n_items) {
     if (rc != SS_OK) return rc;
     CK(e1); CK(e2); CK(e3);
     return SS_OK;
+}
+
+extern "C" int ss_render_host(ss_ctx* c, const ss_source* items, int n_items) {
+    return ss_render_host_ex(c, items, n_items, nullptr);
 }
 
 extern "C" int ss_convolve_fixed_receiver(ss_ctx* c, const float* x, const float* rirs, float* out,

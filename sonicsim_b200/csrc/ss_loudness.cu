@@ -1,0 +1,169 @@
+// sonicsim_b200 :: ss_loudness.cu - SonicSim_audio.lufs_norm (SonicSim_audio.py:68-81) on the GPU.
+//   k_kweight_energy : one thread per (stem, channel, elementary interval) runs the two K-weighting
+//                      biquads in float64 over its interval (+ warm-up) and accumulates the energy
+//   k_loud_gate      : one thread per stem: block loudness, absolute / relative gates, LUFS, gain
+//   k_loud_scale     : out = gain * data (float4 vectorised)
+#include <math.h>
+#include <string.h>
+
+#include "ss_internal.h"
+#include "ss_loud.cuh"
+
+using namespace ss;
+
+__global__ void __launch_bounds__(128)
+k_kweight_energy(const LoudItem* __restrict__ items, const int* __restrict__ prefix, int n_items, KCoef k) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= prefix[n_items]) return;
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (prefix[mid] <= gid) lo = mid; else hi = mid - 1; }
+    const LoudItem& it = items[lo];
+    const int local = gid - prefix[lo];
+    const int c = local / it.n_e, e = local - c * it.n_e;
+    it.E[(long long)c * it.n_e + e] = kweight_interval_energy(it, k, c, e);
+}
+
+__global__ void k_loud_gate(const LoudItem* __restrict__ items, int n_items) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_items) loudness_gate(items[i]);
+}
+
+__global__ void __launch_bounds__(256)
+k_loud_scale(const LoudItem* __restrict__ items) {
+    const LoudItem& it = items[blockIdx.y];
+    if (!it.out) return;
+    const float g = (float)it.result[1];
+    const long long total = (long long)it.N * it.C;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((uintptr_t)it.data | (uintptr_t)it.out) & 15) == 0) {
+        const long long n4 = total >> 2;
+        const float4* s = (const float4*)it.data; float4* d = (float4*)it.out;
+        for (long long q = i; q < n4; q += stride) { float4 v = s[q]; v.x *= g; v.y *= g; v.z *= g; v.w *= g; d[q] = v; }
+        for (long long q = (n4 << 2) + i; q < total; q += stride) it.out[q] = it.data[q] * g;
+    } else {
+        for (long long q = i; q < total; q += stride) it.out[q] = it.data[q] * g;
+    }
+}
+
+static int validate_loud(const ss_loud_item& it) {
+    if (!it.data || !it.brk || !it.blk_lo || !it.blk_hi || !it.scratch || !it.result) return SS_ERR_INVALID;
+    if (it.N <= 0 || it.C <= 0 || it.n_e <= 0 || it.n_blocks < 0 || it.rate <= 0) return SS_ERR_INVALID;
+    if (it.C > 8) return SS_ERR_UNSUPPORTED;
+    return SS_OK;
+}
+
+static LoudItem to_item(const ss_loud_item& a) {
+    LoudItem it;
+    memset(&it, 0, sizeof(it));
+    it.data = a.data; it.out = a.out; it.brk = a.brk; it.blk_lo = a.blk_lo; it.blk_hi = a.blk_hi;
+    it.E = a.scratch; it.result = a.result;
+    it.stride_n = a.stride_n; it.stride_c = a.stride_c;
+    it.N = a.N; it.C = a.C; it.n_e = a.n_e; it.n_blocks = a.n_blocks;
+    it.warm = (int)ceil(0.128 * a.rate);
+    it.inv_norm = 1.0 / (a.block_size * a.rate);
+    it.target = a.target_lufs;
+    return it;
+}
+
+// all items must share one sample rate (one set of filter coefficients per launch)
+extern "C" int ss_loudness_dev(ss_ctx* c, const ss_loud_item* items, int n_items, void* stream_) {
+    if (!c || (!items && n_items > 0) || n_items < 0) return SS_ERR_INVALID;
+    if (n_items == 0) return SS_OK;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    for (int i = 0; i < n_items; ++i) {
+        int st = validate_loud(items[i]); if (st) return st;
+        if (items[i].rate != items[0].rate) return SS_ERR_INVALID;
+    }
+    const size_t off_p = align_up(sizeof(LoudItem) * n_items, 16);
+    const size_t bytes = off_p + align_up(sizeof(int) * (n_items + 1), 16);
+    const int slot = c->ring_pos; c->ring_pos = (c->ring_pos + 1) % ss_ctx::kRing;
+    CK(cudaEventSynchronize(c->desc_ev[slot]));
+    if (bytes > c->desc_cap[slot]) {
+        if (c->h_desc[slot]) CK(cudaFreeHost(c->h_desc[slot]));
+        if (c->d_desc[slot]) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->d_desc[slot])); }
+        c->h_desc[slot] = nullptr; c->d_desc[slot] = nullptr; c->desc_cap[slot] = 0;
+        size_t cap = align_up(bytes * 2, 4096);
+        CK(cudaHostAlloc((void**)&c->h_desc[slot], cap, cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&c->d_desc[slot], cap));
+        c->desc_cap[slot] = cap;
+    }
+    LoudItem* h = (LoudItem*)c->h_desc[slot];
+    int* hp = (int*)(c->h_desc[slot] + off_p);
+    int tot = 0; bool any_out = false;
+    for (int i = 0; i < n_items; ++i) {
+        h[i] = to_item(items[i]);
+        hp[i] = tot; tot += h[i].C * h[i].n_e;
+        any_out = any_out || h[i].out != nullptr;
+    }
+    hp[n_items] = tot;
+    CK(cudaMemcpyAsync(c->d_desc[slot], c->h_desc[slot], bytes, cudaMemcpyHostToDevice, stream));
+    CK(cudaEventRecord(c->desc_ev[slot], stream));
+    const LoudItem* d = (const LoudItem*)c->d_desc[slot];
+    const int* dp = (const int*)(c->d_desc[slot] + off_p);
+    const KCoef k = make_kcoef(items[0].rate);
+    k_kweight_energy<<<(tot + 127) / 128, 128, 0, stream>>>(d, dp, n_items, k);
+    CK(cudaGetLastError());
+    k_loud_gate<<<(n_items + 63) / 64, 64, 0, stream>>>(d, n_items);
+    CK(cudaGetLastError());
+    c->launches += 2;
+    if (any_out) {
+        dim3 grid(c->sm_count * 2, n_items);
+        k_loud_scale<<<grid, 256, 0, stream>>>(d);
+        CK(cudaGetLastError());
+        c->launches += 1;
+    }
+    return SS_OK;
+}
+
+// Single stem, host arrays (the drop-in lufs_norm): data / out hold N*C floats in the caller's layout.
+extern "C" int ss_lufs_norm_host(ss_ctx* c, const float* data, float* out, int32_t N, int32_t C,
+                                 int64_t stride_n, int64_t stride_c, double rate, double block_size,
+                                 double target_lufs, const int32_t* brk, int32_t n_e, const int32_t* blk_lo,
+                                 const int32_t* blk_hi, int32_t n_blocks, double* loudness, double* gain) {
+    if (!c || !data || !brk || !blk_lo || !blk_hi || N <= 0 || C <= 0 || n_e <= 0) return SS_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const size_t nel = (size_t)N * C;
+    const size_t o_data = 0;
+    const size_t o_brk = align_up(nel * 4, 256);
+    const size_t o_lo = o_brk + align_up(4 * (size_t)(n_e + 1), 256);
+    const size_t o_hi = o_lo + align_up(4 * (size_t)(n_blocks + 1), 256);
+    const size_t o_E = o_hi + align_up(4 * (size_t)(n_blocks + 1), 256);
+    const size_t o_res = o_E + align_up(8 * (size_t)C * n_e, 256);
+    const size_t total = o_res + 256;
+    ss_ctx::Slot& sl = c->slot[0];
+    CK(cudaStreamSynchronize(c->s_cmp));
+    if (total > sl.in_cap) {
+        CK(cudaDeviceSynchronize());
+        if (sl.d_in) CK(cudaFree(sl.d_in));
+        sl.d_in = nullptr; sl.in_cap = 0;
+        CK(cudaMalloc((void**)&sl.d_in, align_up(total, 1 << 20)));
+        sl.in_cap = align_up(total, 1 << 20);
+    }
+    char* base = sl.d_in;
+    cudaStream_t st = c->s_cmp;
+    CK(cudaMemcpyAsync(base + o_data, data, nel * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_brk, brk, 4 * (size_t)(n_e + 1), cudaMemcpyHostToDevice, st));
+    if (n_blocks > 0) {
+        CK(cudaMemcpyAsync(base + o_lo, blk_lo, 4 * (size_t)n_blocks, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(base + o_hi, blk_hi, 4 * (size_t)n_blocks, cudaMemcpyHostToDevice, st));
+    }
+    ss_loud_item it;
+    memset(&it, 0, sizeof(it));
+    it.data = (const float*)(base + o_data);
+    it.out = out ? (float*)(base + o_data) : nullptr;       // scaled in place on the device
+    it.brk = (const int32_t*)(base + o_brk); it.blk_lo = (const int32_t*)(base + o_lo); it.blk_hi = (const int32_t*)(base + o_hi);
+    it.scratch = (double*)(base + o_E); it.result = (double*)(base + o_res);
+    it.stride_n = stride_n; it.stride_c = stride_c; it.N = N; it.C = C; it.n_e = n_e; it.n_blocks = n_blocks;
+    it.rate = rate; it.block_size = block_size; it.target_lufs = target_lufs;
+    int rc = ss_loudness_dev(c, &it, 1, (void*)st);
+    if (rc) return rc;
+    double res[2];
+    CK(cudaMemcpyAsync(res, base + o_res, sizeof(res), cudaMemcpyDeviceToHost, st));
+    if (out) CK(cudaMemcpyAsync(out, base + o_data, nel * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (loudness) *loudness = res[0];
+    if (gain) *gain = res[1];
+    return SS_OK;
+}

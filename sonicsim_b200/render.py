@@ -11,7 +11,7 @@ import typing as T
 import numpy as np
 
 from . import _lib
-from ._lib import SsSource
+from ._lib import SsPostLufs, SsSource
 from .SonicSim_moving import _as_f32, _samples_per_interval, bounds_from_counts
 
 
@@ -38,10 +38,18 @@ class Renderer:
 
     # ------------------------------------------------------------------ host buffers
     def render_host(self, sources: T.Sequence[T.Union[MovingSource, StaticSource]],
-                    outs: T.Optional[T.Sequence[np.ndarray]] = None) -> T.List[np.ndarray]:
-        """Render every source; returns a list of (C, N) float32 arrays (pinned `outs` may be passed)."""
+                    outs: T.Optional[T.Sequence[np.ndarray]] = None,
+                    lufs_targets: T.Optional[T.Sequence[T.Optional[float]]] = None, sr: float = 16000,
+                    loudness_out: T.Optional[list] = None) -> T.List[np.ndarray]:
+        """Render every source; returns a list of (C, N) float32 arrays (pinned `outs` may be passed).
+        `lufs_targets[i]` (or None) additionally normalises stem i to that integrated loudness on
+        the device before the copy out - SonicSim_audio.lufs_norm fused behind the render
+        (SonicSet.py:97-101).  `loudness_out`, if a list, receives (measured LUFS, linear gain) per source."""
+        from .SonicSim_audio import gating_plan
         n = len(sources)
         items = (SsSource * n)()
+        post = (SsPostLufs * n)() if lufs_targets is not None else None
+        results_l = np.full((n, 2), np.nan, dtype=np.float64)
         keep = []
         results = []
         for i, s in enumerate(sources):
@@ -66,7 +74,21 @@ class Renderer:
                                 N=N, P=P, C=C, L=L, mode=mode)
             keep.append((x, h, bounds, out))
             results.append(out)
-        _lib.check(self.lib.ss_render_host(self.ctx, items, n))
+            if post is not None and lufs_targets[i] is not None:
+                if C > 8:
+                    raise ValueError("loudness normalisation supports at most 8 channels")
+                block = 0.4 if N / sr >= 0.4 else N / sr                      # SonicSim_audio.py:69
+                brk, blo, bhi = gating_plan(N, float(sr), float(block))
+                post[i] = SsPostLufs(brk=brk.ctypes.data, blk_lo=blo.ctypes.data, blk_hi=bhi.ctypes.data,
+                                     n_e=len(brk) - 1, n_blocks=len(blo), rate=float(sr), block_size=float(block),
+                                     target_lufs=float(lufs_targets[i]), result=results_l[i].ctypes.data)
+                keep.append((brk, blo, bhi))
+        if post is None:
+            _lib.check(self.lib.ss_render_host(self.ctx, items, n))
+        else:
+            _lib.check(self.lib.ss_render_host_ex(self.ctx, items, n, post))
+            if loudness_out is not None:
+                loudness_out[:] = [tuple(r) for r in results_l]
         return results
 
     # ------------------------------------------------------------------ device tensors
@@ -132,11 +154,24 @@ def convolve_moving(dry_list, rirs_list, positions_list) -> T.List[np.ndarray]:
     return default_renderer().render_host(srcs)
 
 
-def render_scene(moving: T.Sequence[T.Tuple], static: T.Sequence[T.Tuple] = ()) -> T.Tuple[T.List[np.ndarray], T.List[np.ndarray]]:
-    """One scene of SonicSet.process_single (SonicSet.py:77-94) in a single call:
+def render_scene(moving: T.Sequence[T.Tuple], static: T.Sequence[T.Tuple] = (), sr: float = 16000,
+                 moving_lufs: T.Optional[float] = None, static_lufs: T.Optional[T.Sequence[float]] = None
+                 ) -> T.Tuple[T.List[np.ndarray], T.List[np.ndarray]]:
+    """One scene of SonicSet.process_single (SonicSet.py:77-101) in a single call:
     `moving` = [(dry (N,), rirs (P, C, L), positions (P, 3)), ...], `static` = [(dry (N,), rir (C, L)), ...].
+    With `moving_lufs` (SonicSet uses -17) / `static_lufs` (SonicSet: [-24, -29] for noise, music) every
+    stem is loudness-normalised like get_lufs_norm_audio: target ~ U(lufs - 2, lufs + 2) from the global
+    NumPy RNG, drawn in the reference's order (all moving stems, then the static ones).
     Returns (moving stems, static stems), each (C, N) float32."""
     srcs: T.List = [MovingSource(d, r, trajectory_bounds(p, np.asarray(d).shape[-1])) for d, r, p in moving]
     srcs += [StaticSource(d, r) for d, r in static]
-    outs = default_renderer().render_host(srcs)
+    targets = None
+    if moving_lufs is not None or static_lufs is not None:
+        targets = []
+        for _ in moving:
+            targets.append(None if moving_lufs is None else np.random.uniform(moving_lufs - 2, moving_lufs + 2))
+        for i, _ in enumerate(static):
+            l = None if static_lufs is None else static_lufs[i]
+            targets.append(None if l is None else np.random.uniform(l - 2, l + 2))
+    outs = default_renderer().render_host(srcs, lufs_targets=targets, sr=sr)
     return outs[: len(moving)], outs[len(moving):]

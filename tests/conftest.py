@@ -75,9 +75,22 @@ def emu():
         lib.emu_spectra_pair(ptr(a), ptr(b), a.shape[0], ptr(sa), ptr(sb))
         return sa.view(np.complex64), sb.view(np.complex64)
 
+    def lufs(data, rate, block_size, target=-20.0):
+        from sonicsim_b200.SonicSim_audio import gating_plan
+        x = np.ascontiguousarray(data, np.float32)
+        N = x.shape[0]
+        C = 1 if x.ndim == 1 else x.shape[1]
+        brk, lo, hi = gating_plan(N, float(rate), float(block_size))
+        res = np.zeros(2, np.float64)
+        lib.emu_lufs(ptr(x), N, C, ctypes.c_longlong(C), ctypes.c_longlong(1), ctypes.c_double(rate),
+                     ctypes.c_double(block_size), ctypes.c_double(target), ptr(brk, ip), len(brk) - 1,
+                     ptr(lo, ip), ptr(hi, ip), len(lo), res.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        return float(res[0]), float(res[1])
+
     class Emu:
         pass
     e = Emu()
     e.render = render
     e.spectra_pair = spectra_pair
+    e.lufs = lufs
     return e

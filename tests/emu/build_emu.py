@@ -7,7 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(HERE, "ss_emu.cu")
 OUT = os.path.join(HERE, "libss_emu.so")
 DEPS = [SRC, os.path.join(ROOT, "sonicsim_b200", "csrc", "ss_core.cuh"),
-        os.path.join(ROOT, "sonicsim_b200", "csrc", "ss_phases.cuh")]
+        os.path.join(ROOT, "sonicsim_b200", "csrc", "ss_phases.cuh"),
+        os.path.join(ROOT, "sonicsim_b200", "csrc", "ss_loud.cuh")]
 
 
 def build(force=False):

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../sonicsim_b200/csrc/ss_phases.cuh"
+#include "../../sonicsim_b200/csrc/ss_loud.cuh"
 
 using namespace ss;
 
@@ -139,6 +140,21 @@ int emu_spectra_pair(const float* a, const float* b, int len, float* specA, floa
     // return partition 0 of each row
     memcpy(specA, hs.data(), sizeof(float2) * kSpec);
     memcpy(specB, hs.data() + (size_t)S.K * kSpec, sizeof(float2) * kSpec);
+    return 0;
+}
+
+// loudness: k_kweight_energy + k_loud_gate, one emulated thread per (channel, interval)
+int emu_lufs(const float* data, int N, int C, long long stride_n, long long stride_c, double rate, double block_size,
+             double target, const int32_t* brk, int n_e, const int32_t* blk_lo, const int32_t* blk_hi, int n_blocks,
+             double* result) {
+    LoudItem it; memset(&it, 0, sizeof(it));
+    std::vector<double> E((size_t)C * n_e);
+    it.data = data; it.brk = brk; it.blk_lo = blk_lo; it.blk_hi = blk_hi; it.E = E.data(); it.result = result;
+    it.stride_n = stride_n; it.stride_c = stride_c; it.N = N; it.C = C; it.n_e = n_e; it.n_blocks = n_blocks;
+    it.warm = (int)ceil(0.128 * rate); it.inv_norm = 1.0 / (block_size * rate); it.target = target;
+    KCoef k = make_kcoef(rate);
+    for (int c = 0; c < C; ++c) for (int e = 0; e < n_e; ++e) E[(size_t)c * n_e + e] = kweight_interval_energy(it, k, c, e);
+    loudness_gate(it);
     return 0;
 }
 

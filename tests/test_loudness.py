@@ -1,0 +1,123 @@
+"""lufs_norm (SonicSim_audio.py:68-81): oracle (pyloudnorm 0.1.1 restatement, "parity unpinned")
+against the kernels' per-thread code (CPU emulation) and, with -m gpu, the CUDA path."""
+import numpy as np
+import pytest
+
+from oracle import sonicsim_oracle as so
+
+
+def stems(seed, N, C, sr=16000):
+    rng = np.random.default_rng(seed)
+    t = np.arange(N) / sr
+    env = 0.5 + 0.5 * np.sin(2 * np.pi * 0.7 * t + rng.random() * 6)          # loud / quiet passages exercise the gates
+    x = rng.standard_normal((N, C)) * env[:, None] * 0.05
+    x[: N // 7] *= 1e-4                                                        # a near-silent lead-in (absolute gate)
+    x += 0.02 * np.sin(2 * np.pi * 30 * t)[:, None]                            # sub-38 Hz content (high-pass matters)
+    return x.astype(np.float32)
+
+
+def test_oracle_kweighting_reference_values():
+    """Pins of the restatement that do not need pyloudnorm: BS.1770's own 48 kHz coefficient table
+    and the standard's -3.01 LKFS for a 0 dBFS 997 Hz sine (+3.01 for two channels)."""
+    (b1, a1), (b2, a2) = so.bs1770_k_weighting(48000)
+    assert np.allclose(b1, [1.53512485958697, -2.69169618940638, 1.19839281085285], atol=2e-3)
+    assert np.allclose(a1, [1.0, -1.69065929318241, 0.73248077421585], atol=2e-3)
+    assert np.allclose(b2, [1.0, -2.0, 1.0], atol=1.1e-2)      # RBJ form is a0-normalised: 0.995 * [1, -2, 1]
+    assert np.allclose(a2, [1.0, -1.99004745483398, 0.99007225036621], atol=1e-4)
+    sr = 48000
+    t = np.arange(sr * 5) / sr
+    sine = np.sin(2 * np.pi * 997 * t).astype(np.float32)
+    assert abs(so.bs1770_integrated_loudness(sine, sr) - (-3.01)) < 0.05
+    assert abs(so.bs1770_integrated_loudness(np.stack([sine, sine], 1), sr) - 0.0) < 0.05
+
+
+@pytest.mark.parametrize("N,C,sr", [(160000, 2, 16000), (48000, 1, 16000), (5000, 2, 16000), (96000, 5, 48000),
+                                    (6400, 1, 16000), (100001, 3, 16000)])
+def test_emulated_kernels_match_oracle(emu, N, C, sr):
+    x = stems(N + C, N, C, sr)
+    block = 0.4 if N / sr >= 0.4 else N / sr
+    ref = so.bs1770_integrated_loudness(x, sr, block)
+    got, gain = emu.lufs(x, sr, block, target=-23.0)
+    assert abs(got - ref) < 1e-4, (got, ref)                    # 1e-4 dB -> 1.2e-5 relative gain error
+    assert abs(gain - 10 ** ((-23.0 - ref) / 20)) / gain < 2e-5
+
+
+def test_silence_maps_to_minus_40(emu):
+    x = np.zeros((16000, 2), np.float32)
+    lufs, gain = emu.lufs(x, 16000, 0.4, target=-17.0)
+    assert np.isinf(lufs) and lufs < 0
+    assert abs(gain - 10 ** ((-17.0 + 40.0) / 20)) < 1e-9       # SonicSim_audio.py:73-75
+    with np.errstate(all="ignore"):
+        y, g = so.lufs_norm(x, 16000, -17.0)
+    assert g == 0.0 and not y.any()
+
+
+def test_gating_plan_matches_pyloudnorm_expressions():
+    from sonicsim_b200.SonicSim_audio import gating_plan
+    for N, sr, bs in [(960000, 16000, 0.4), (100001, 16000, 0.4), (2880000, 48000, 0.4), (5000, 16000, 5000 / 16000)]:
+        lo, hi = so.bs1770_block_bounds(N, sr, bs)
+        brk, blo, bhi = gating_plan(N, float(sr), float(bs))
+        assert np.array_equal(brk[blo], np.minimum(lo, N)) and np.array_equal(brk[bhi], np.minimum(hi, N))
+        assert np.all(np.diff(brk) > 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,C", [(480000, 2), (960000, 1), (100001, 5), (5000, 2)])
+def test_gpu_lufs_norm_matches_oracle(N, C):
+    from sonicsim_b200 import SonicSim_audio as sa
+    x = stems(7 * N + C, N, C)
+    y_ref, g_ref = so.lufs_norm(x, 16000, -17.0)
+    y, g = sa.lufs_norm(x, 16000, -17.0)
+    assert y.dtype == np.float32 and y.shape == x.shape
+    assert so.rel_rms(y, y_ref) < 1e-4
+    assert abs(g - g_ref) / abs(g_ref) < 1e-3
+    np.random.seed(3)
+    y2, _ = sa.get_lufs_norm_audio(x, 16000, -24)
+    np.random.seed(3)
+    y2_ref, _ = so.get_lufs_norm_audio(x, 16000, -24)
+    assert so.rel_rms(y2, y2_ref) < 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_lufs_errors_like_pyloudnorm():
+    from sonicsim_b200 import SonicSim_audio as sa
+    with pytest.raises(ValueError):
+        sa.lufs_norm(np.zeros((16000, 6), np.float32), 16000, -17)      # > 5 channels
+    with pytest.raises(ValueError):
+        sa.lufs_norm(np.zeros((16000, 2), np.int16), 16000, -17)
+
+
+@pytest.mark.gpu
+def test_gpu_fft_conv_golden(golden):
+    import torch
+    from sonicsim_b200 import SonicSim_audio as sa
+    g = golden("fft_conv")
+    for k in range(int(g["n_cases"])):
+        y = sa.fft_conv(torch.from_numpy(g[f"x{k}"]), torch.from_numpy(g[f"h{k}"]), is_cpu=True)
+        assert isinstance(y, torch.Tensor) and y.shape == torch.Size(g[f"y{k}"].shape)
+        assert so.rel_rms(y.numpy(), g[f"y{k}"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_render_scene_with_loudness_matches_reference_pipeline():
+    """SonicSet.py:77-101: render 2 moving + 2 static stems, then get_lufs_norm_audio on each."""
+    from sonicsim_b200 import render
+    rng = np.random.default_rng(77)
+    N, C, L, P = 64000, 2, 1500, 5
+    moving = [(so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L), so.synth_path(rng, P)) for _ in range(2)]
+    static = [(so.synth_dry(rng, N), so.synth_rirs(rng, 1, C, L)[0]) for _ in range(2)]
+    np.random.seed(123)
+    ym, ys = render.render_scene(moving, static, sr=16000, moving_lufs=-17, static_lufs=[-24, -29])
+    # the reference's order of RNG draws: trajectories first (interpolate_moving_audio), then the targets
+    np.random.seed(123)
+    stems_ref = []
+    for x, h, pos in moving:
+        idx, w = so.setup_dynamic_interp(pos, N)
+        stems_ref.append(so.convolve_moving_receiver(x, h, idx, w))
+    for x, h in static:
+        stems_ref.append(so.convolve_fixed_receiver(x[None], h))
+    refs = []
+    for stem, l in zip(stems_ref, [-17, -17, -24, -29]):
+        refs.append(so.get_lufs_norm_audio(np.ascontiguousarray(stem.T), 16000, l)[0].T)
+    for y, r in zip(ym + ys, refs):
+        assert so.rel_rms(y, r) < 1e-4
