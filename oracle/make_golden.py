@@ -96,13 +96,14 @@ def main():
 
     # ---- a6: fft_conv (torch.fft)
     cases = {}
-    for k, (seed, L, N) in enumerate([(51, 200, 3000), (52, 4096, 6000)]):
+    for k, (seed, L, N) in enumerate([(51, 200, 3000), (52, 4096, 6000),          # N+L-1 odd: the reference's irfftn returns N+L-2 resampled samples
+                                      (53, 200, 3001), (54, 4096, 6001)]):        # N+L-1 even: a true full convolution
         rng = np.random.default_rng(seed)
         x = so.synth_dry(rng, N)
         h = so.synth_rirs(rng, 1, 1, L)[0, 0]
         y = ref_audio.fft_conv(torch.from_numpy(x), torch.from_numpy(h), is_cpu=True)
         cases[f"x{k}"], cases[f"h{k}"], cases[f"y{k}"] = x, h, y.numpy()
-    cases["n_cases"] = np.int64(2)
+    cases["n_cases"] = np.int64(4)
     np.savez_compressed(os.path.join(OUT, "fft_conv.npz"), **cases)
 
     for f in sorted(os.listdir(OUT)):

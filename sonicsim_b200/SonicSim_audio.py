@@ -87,12 +87,27 @@ def get_lufs_norm_audio(audio, sr=16000, lufs=-6):
 
 # ------------------------------------------------------------------------------------ fft_conv
 def fft_conv(signal, kernel, is_cpu: bool = False):
-    """SonicSim_audio.py:17-47: full linear convolution of two 1-D tensors, length N + L - 1.
-    (The reference zero-pads both to N + L - 1 and multiplies rfftn spectra; the CUDA path runs
-    the same product as a static overlap-save render of the zero-extended signal.)"""
+    """SonicSim_audio.py:17-47: zero-pad both to M = N + L - 1, rfftn * rfftn -> irfftn.
+
+    M even: the result is the full linear convolution (length M); it runs on the CUDA renderer as a
+    static overlap-save render of the zero-extended signal.
+    M odd: the reference calls `irfftn` without a length, which returns M - 1 samples of the
+    band-limited interpolant of the convolution resampled at stride M / (M - 1) - not a convolution
+    (rel. error 0.7-0.9 against one).  `fft_conv` is dead code on the SonicSet path; for
+    fidelity this quirk is reproduced with the same torch.fft calls on the CUDA device rather than
+    with a kernel of our own."""
     import torch
     from .SonicSim_moving import convolve_fixed_receiver
     dev = signal.device
+    n_sig, n_ker = signal.numel(), kernel.numel()
+    if (n_sig + n_ker - 1) % 2 == 1:
+        import torch.nn.functional as F
+        if not torch.cuda.is_available():
+            raise RuntimeError("sonicsim_b200.fft_conv needs a CUDA device (no CPU fallback)")
+        s = F.pad(signal.detach().reshape(-1).to("cuda", torch.float32), (0, n_ker - 1))
+        k = F.pad(kernel.detach().reshape(-1).to("cuda", torch.float32), (0, n_sig - 1))
+        out = torch.fft.irfftn(torch.fft.rfftn(s, dim=-1) * torch.fft.rfftn(k, dim=-1), dim=-1)
+        return out.cpu() if is_cpu else out.to(dev)
     x = signal.detach().reshape(-1).to("cpu", torch.float32).numpy()
     h = kernel.detach().reshape(-1).to("cpu", torch.float32).numpy()
     xp = np.concatenate([x, np.zeros(h.shape[0] - 1, np.float32)])

@@ -60,7 +60,10 @@ k_spectra(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n
 }
 
 // ----------------------------------------------------------------------------- k_render
-__global__ void __launch_bounds__(kThreads, 2)
+#ifndef SS_RENDER_MINB
+#define SS_RENDER_MINB 2
+#endif
+__global__ void __launch_bounds__(kThreads, SS_RENDER_MINB)
 k_render(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_src) {
     extern __shared__ float2 smem[];
     __shared__ int s_red[2 * (kThreads / 32)];
