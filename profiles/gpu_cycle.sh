@@ -15,5 +15,5 @@ PY
 tail -3 gpurun_out/bench_$TAG.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --utterances 4 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_render -s 2 -c 1 -o gpurun_out/prof_render_$TAG python bench.py --steps 1 --warmup 3 --utterances 4 --no-cpu-baseline > gpurun_out/ncu_render.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_spectra -s 2 -c 1 -o gpurun_out/prof_spectra_$TAG python bench.py --steps 1 --warmup 3 --utterances 4 --no-cpu-baseline > gpurun_out/ncu_spectra.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_prepare -s 2 -c 1 -o gpurun_out/prof_spectra_$TAG python bench.py --steps 1 --warmup 3 --utterances 4 --no-cpu-baseline > gpurun_out/ncu_spectra.log 2>&1
 ls gpurun_out | tr '\n' ' '

@@ -30,9 +30,14 @@ __device__ float2 g_tw[kF];          // exp(-2 pi i m / 8192)
 __device__ float2 g_twB[kTabB];      // [r][k] exp(-2 pi i k r / 256)
 __device__ float2 g_twC[kTabC];      // [r][k] exp(-2 pi i k r / 4096)
 
-// ----------------------------------------------------------------------------- k_spectra
+// ----------------------------------------------------------------------------- k_prepare
+// CTA kinds, flattened per source through `prefix`:
+//   [0, nh)            two RIR-partition rows  -> two half spectra (one complex FFT)
+//   [nh, nh + nx)      two dry windows         -> two half spectra
+//   [nh + nx, ...)     8 output blocks each (one warp per block): position range of the block and
+//                      its k_render work items (RItem)
 __global__ void __launch_bounds__(kThreads, 2)
-k_spectra(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_src) {
+k_prepare(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_src) {
     extern __shared__ float2 smem[];
     const Tables T{g_tw, g_twB, g_twC};
     const int t = threadIdx.x;
@@ -40,7 +45,31 @@ k_spectra(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n
     const Source& S = srcs[si];
     int local = blockIdx.x - prefix[si];
     Row ra, rb;
-    const int nh = spectra_pairs_h(S);
+    const int nh = spectra_pairs_h(S), nx = spectra_pairs_x(S);
+    if (local >= nh + nx) {
+        const int b = (local - nh - nx) * 8 + (t >> 5), lane = t & 31;
+        if (b >= S.nb) return;
+        const int n0 = b * kB;
+        const int n_last = (n0 + kB < S.N ? n0 + kB : S.N) - 1;
+        int p_lo = 0, p_hi = 0;
+        if (S.mode == MODE_MOVING_BOUNDS) {
+            p_lo = seg_of(S.bounds, S.P - 1, n0);
+            p_hi = seg_of(S.bounds, S.P - 1, n_last) + 1;
+        } else if (S.mode == MODE_MOVING_INDEXED) {
+            int pmin = 0x7fffffff, pmax = -1;
+            for (int n = n0 + lane; n <= n_last; n += 32) { int v = S.idx[n]; pmin = v < pmin ? v : pmin; pmax = v > pmax ? v : pmax; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                int a = __shfl_xor_sync(0xffffffffu, pmin, o), bm = __shfl_xor_sync(0xffffffffu, pmax, o);
+                pmin = a < pmin ? a : pmin; pmax = bm > pmax ? bm : pmax;
+            }
+            // the reference raises IndexError for idx + 1 >= P (checked on the host path); clamp here
+            p_lo = pmin < 0 ? 0 : pmin;
+            p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
+        }
+        fill_items(S, si, b, p_lo, p_hi, lane, 32);
+        return;
+    }
     if (local < nh) { ra = make_row_h(S, 2 * local); rb = make_row_h(S, 2 * local + 1); }
     else { local -= nh; ra = make_row_x(S, 2 * local); rb = make_row_x(S, 2 * local + 1); }
 
@@ -60,84 +89,142 @@ k_spectra(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n
 }
 
 // ----------------------------------------------------------------------------- k_render
+// mbarrier / bulk-copy (TMA engine, 1-D) helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kSpecBytes = kSpec * (int)sizeof(float2);                       // 32 KB
+constexpr int kRenderSmem = kPadF * (int)sizeof(float2) + kSpecBytes;         // FFT buffer + Hq staging
+
 #ifndef SS_RENDER_MINB
 #define SS_RENDER_MINB 2
 #endif
+// Persistent CTAs: CTA i renders items i, i + gridDim.x, ...  Thread 0 runs one transform ahead:
+// while the CTA computes transform k it has the bulk-copy engine stage transform k+1's spectra —
+// Hq into the staging buffer as soon as form_z(k) has consumed it, X and Hp into the FFT buffer itself
+// once pass C of transform k has read it out — so form_z never waits on L2.
 __global__ void __launch_bounds__(kThreads, SS_RENDER_MINB)
-k_render(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_src) {
-    extern __shared__ float2 smem[];
-    __shared__ int s_red[2 * (kThreads / 32)];
+k_render(const Source* __restrict__ srcs, const RItem* __restrict__ items, int n_items) {
+    extern __shared__ __align__(128) float2 smem[];
+    __shared__ __align__(16) RItem s_item[2];
+    __shared__ __align__(16) XDesc s_desc[2];
+    __shared__ __align__(8) uint64_t s_bar[2];          // [0]: X + Hp landed, [1]: Hq landed
+    float2* const fftbuf = smem;
+    float2* const sX = smem;
+    float2* const sHp = smem + kSpec;
+    float2* const sHq = smem + kPadF;
     const Tables T{g_tw, g_twB, g_twC};
     const int t = threadIdx.x;
-    const int si = find_source(prefix, n_src, blockIdx.x);
-    const Source& S = srcs[si];
-    const int local = blockIdx.x - prefix[si];
-    const int mode = S.mode;
 
-    // decode the work item: block b, output row(s), range of transforms
-    int b, c, p_lo, p_hi, sg0 = 0;
-    if (mode == MODE_STATIC) {
-        const int ncp = (S.C + 1) >> 1;
-        b = local / ncp; c = 2 * (local - b * ncp);
-        p_lo = 0; p_hi = 0;
-    } else {
-        b = local / S.C; c = local - b * S.C;
-    }
-    const int n0 = b * kB;
-    if (mode == MODE_MOVING_BOUNDS) {
-        // two lanes search the block's first / last segment, everyone else walks from there
-        if (t < 2) {
-            const int n_last = (n0 + kB < S.N ? n0 + kB : S.N) - 1;
-            s_red[t] = seg_of(S.bounds, S.P - 1, t == 0 ? n0 : n_last);
+    // thread-0 iterator state
+    int it_cur = blockIdx.x;          // item of the transform most recently published
+    int slot = 0;                     // s_item slot holding it
+    int p_cur = 0;
+
+    if (t == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        XDesc d; d.valid = 0;
+        if (it_cur < n_items) {
+            s_item[0] = items[it_cur];
+            if (it_cur + (int)gridDim.x < n_items) s_item[1] = items[it_cur + gridDim.x];
+            p_cur = s_item[0].p_lo;
+            d = make_xdesc(s_item[0], p_cur);
         }
-        __syncthreads();
-        p_lo = s_red[0];
-        p_hi = s_red[1] + 1;
-        const int nn = n0 + t < S.N ? n0 + t : S.N - 1;
-        sg0 = p_lo;
-        while (S.bounds[sg0 + 1] <= nn) ++sg0;
-    } else if (mode == MODE_MOVING_INDEXED) {
-        int pmin, pmax;
-        idx_range(t, n0, S, pmin, pmax);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            int a = __shfl_xor_sync(0xffffffffu, pmin, o), bmax = __shfl_xor_sync(0xffffffffu, pmax, o);
-            pmin = a < pmin ? a : pmin; pmax = bmax > pmax ? bmax : pmax;
-        }
-        if ((t & 31) == 0) { s_red[t >> 5] = pmin; s_red[8 + (t >> 5)] = pmax; }
-        __syncthreads();
-        pmin = s_red[0]; pmax = s_red[8];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) { pmin = s_red[i] < pmin ? s_red[i] : pmin; pmax = s_red[8 + i] > pmax ? s_red[8 + i] : pmax; }
-        // the reference raises IndexError for idx + 1 >= P (checked on the host path); clamp here
-        p_lo = pmin < 0 ? 0 : pmin;
-        p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
+        s_desc[0] = d;
+        fence_proxy_async();
+        if (d.valid) {
+            mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
+            bulk_g2s(sX, d.X, kSpecBytes, &s_bar[0]);
+            bulk_g2s(sHp, d.Hp, kSpecBytes, &s_bar[0]);
+            if (d.Hq) { mbar_expect_tx(&s_bar[1], kSpecBytes); bulk_g2s(sHq, d.Hq, kSpecBytes, &s_bar[1]); }
+            else mbar_arrive(&s_bar[1]);
+        } else { mbar_arrive(&s_bar[0]); mbar_arrive(&s_bar[1]); }
     }
-    const float2* X0 = S.xspec + (size_t)b * kSpec;
-    float* row = S.out + (size_t)c * S.N;
+    __syncthreads();
+
     Regs32 R;
-    for (int p = p_lo; p <= p_hi; p += 2) {
-        const float2 *Hp, *Hq;
-        if (mode == MODE_STATIC) {
-            Hp = S.hspec + (size_t)c * S.K * kSpec;
-            Hq = (c + 1 < S.C) ? Hp + (size_t)S.K * kSpec : nullptr;
-        } else {
-            Hp = S.hspec + ((size_t)p * S.C + c) * S.K * kSpec;
-            Hq = (p + 1 <= p_hi) ? Hp + (size_t)S.C * S.K * kSpec : nullptr;
+    for (int k = 0;; ++k) {
+        mbar_wait(&s_bar[0], k & 1);
+        mbar_wait(&s_bar[1], k & 1);
+        const XDesc& d = s_desc[k & 1];
+        if (!d.valid) break;
+        const Source& S = srcs[d.si];
+        form_z(t, sX, sHp, d.Hq ? sHq : nullptr, d, S.K, R);
+        __syncthreads();                              // staged spectra consumed, s_desc[k & 1] read by all
+        if (t == 0) {
+            // publish transform k+1 and start staging its Hq
+            XDesc nx; nx.valid = 0;
+            const RItem& cur = s_item[slot];
+            if (p_cur + 2 <= cur.p_hi) { p_cur += 2; nx = make_xdesc(cur, p_cur); }
+            else if (it_cur + (int)gridDim.x < n_items) {
+                it_cur += gridDim.x; slot ^= 1;
+                p_cur = s_item[slot].p_lo;
+                nx = make_xdesc(s_item[slot], p_cur);
+                if (it_cur + (int)gridDim.x < n_items) s_item[slot ^ 1] = items[it_cur + gridDim.x];   // look-ahead load
+            }
+            s_desc[(k + 1) & 1] = nx;
+            fence_proxy_async();
+            if (nx.valid && nx.Hq) { mbar_expect_tx(&s_bar[1], kSpecBytes); bulk_g2s(sHq, nx.Hq, kSpecBytes, &s_bar[1]); }
+            else mbar_arrive(&s_bar[1]);
         }
-        form_z(t, X0, b, S.K, Hp, Hq, R);
-        if (p != p_lo) __syncthreads();          // previous transform's pass-C loads are done
-        render_phase1(t, smem, R);
+        render_phase1(t, fftbuf, R);
         __syncthreads();
-        load2(t, smem, R);
+        load2(t, fftbuf, R);
         __syncthreads();
-        passB2<true>(t, smem, R, T);
+        passB2<true>(t, fftbuf, R, T);
         __syncthreads();
-        load2(t, smem, R);
+        load2(t, fftbuf, R);
+        __syncthreads();                              // FFT buffer is free: stage X, Hp of transform k+1 into it
+        if (t == 0) {
+            const XDesc nx = s_desc[(k + 1) & 1];
+            fence_proxy_async();
+            if (nx.valid) {
+                mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
+                bulk_g2s(sX, nx.X, kSpecBytes, &s_bar[0]);
+                bulk_g2s(sHp, nx.Hp, kSpecBytes, &s_bar[0]);
+            } else mbar_arrive(&s_bar[0]);
+        }
         render_phase3(t, R, T);
-        if (mode == MODE_MOVING_BOUNDS) { MovingSinkBounds sk(S, row, n0, t, p, sg0, p == p_lo); render_epilogue(R, sk); }
-        else if (mode == MODE_MOVING_INDEXED) { MovingSinkIndexed sk(S, row, n0, t, p, p == p_lo); render_epilogue(R, sk); }
-        else { StaticSink sk{row, (c + 1 < S.C) ? row + S.N : nullptr, S.N, n0 + t}; render_epilogue(R, sk); }
+        const int n0 = d.b * kB;
+        if (S.mode == MODE_MOVING_BOUNDS) {
+            const int nn = n0 + t < S.N ? n0 + t : S.N - 1;
+            int sg0 = d.p_lo;
+            while (S.bounds[sg0 + 1] <= nn) ++sg0;
+            MovingSinkBounds sk(S, d.row, n0, t, d.p, sg0, d.first != 0);
+            render_epilogue(R, sk);
+        } else if (S.mode == MODE_MOVING_INDEXED) {
+            MovingSinkIndexed sk(S, d.row, n0, t, d.p, d.first != 0);
+            render_epilogue(R, sk);
+        } else {
+            StaticSink sk{d.row, d.Hq ? d.row + S.N : nullptr, S.N, n0 + t};
+            render_epilogue(R, sk);
+        }
     }
 }
 
@@ -186,9 +273,8 @@ extern "C" int ss_create(int device, ss_ctx** out) {
     }
     CK(cudaMemcpyToSymbol(g_twB, tb.data(), sizeof(float2) * kTabB));
     CK(cudaMemcpyToSymbol(g_twC, tc.data(), sizeof(float2) * kTabC));
-    const int smem = kPadF * (int)sizeof(float2);
-    CK(cudaFuncSetAttribute(k_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
+    CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
     for (int i = 0; i < ss_ctx::kRing; ++i) CK(cudaEventCreateWithFlags(&c->desc_ev[i], cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking));
@@ -273,7 +359,8 @@ static int validate_item(const ss_source& it) {
 }
 static size_t spectra_bytes(const ss_source& it) {
     size_t K = (it.L + kB - 1) / kB, nb = (it.N + kB - 1) / kB;
-    return ((size_t)it.P * it.C * K + nb) * kSpec * sizeof(float2);
+    size_t n_items = it.mode == SS_STATIC ? nb * ((it.C + 1) / 2) : nb * (size_t)it.C;
+    return ((size_t)it.P * it.C * K + nb) * kSpec * sizeof(float2) + n_items * sizeof(RItem);
 }
 
 // Enqueue the three launches for items[first, last) (device pointers) on `stream`.
@@ -326,25 +413,28 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
         s.xspec = (float2*)scratch; scratch += (size_t)s.nb * kSpec * sizeof(float2);
         hs[i] = s;
         hps[i] = ps; hpr[i] = pr;
-        ps += spectra_pairs_h(s) + spectra_pairs_x(s);
+        ps += spectra_pairs_h(s) + spectra_pairs_x(s) + range_ctas(s);
         pr += render_ctas(s);
     }
+    // work-item table of the whole chunk, contiguous in source order, after all spectra
+    RItem* d_items = (RItem*)scratch;
+    for (int i = 0; i < n; ++i) hs[i].items = d_items + hpr[i];
     hps[n] = ps; hpr[n] = pr;
     CK(cudaMemcpyAsync(c->d_desc[slot], c->h_desc[slot], bytes, cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(c->desc_ev[slot], stream));
     const Source* ds = (const Source*)c->d_desc[slot];
     const int* dps = (const int*)(c->d_desc[slot] + off_ps);
     const int* dpr = (const int*)(c->d_desc[slot] + off_pr);
-    const int smem = kPadF * (int)sizeof(float2);
     ss_ctx::Prof pf;
     if (c->profiling) {
         CK(cudaEventCreate(&pf.e0)); CK(cudaEventCreate(&pf.e1)); CK(cudaEventCreate(&pf.e2));
         CK(cudaEventRecord(pf.e0, stream));
     }
-    k_spectra<<<ps, kThreads, smem, stream>>>(ds, dps, n);
+    k_prepare<<<ps, kThreads, kPadF * (int)sizeof(float2), stream>>>(ds, dps, n);
     CK(cudaGetLastError());
     if (c->profiling) CK(cudaEventRecord(pf.e1, stream));
-    k_render<<<pr, kThreads, smem, stream>>>(ds, dpr, n);
+    const int grid_r = pr < c->sm_count * SS_RENDER_MINB ? pr : c->sm_count * SS_RENDER_MINB;
+    k_render<<<grid_r, kThreads, kRenderSmem, stream>>>(ds, d_items, pr);
     CK(cudaGetLastError());
     if (c->profiling) { CK(cudaEventRecord(pf.e2, stream)); c->prof.push_back(pf); }
     c->launches += 2;

@@ -9,6 +9,8 @@
 
 namespace ss {
 
+enum { MODE_STATIC = 0, MODE_MOVING_BOUNDS = 1, MODE_MOVING_INDEXED = 2 };
+
 // One (utterance, source) unit.  Reference shapes: dry (N,), RIRs (P, C, L), output (C, N)
 // (SonicSim_moving.py:63-96); static source has P = 1 (SonicSim_moving.py:47-61).
 struct Source {
@@ -20,14 +22,89 @@ struct Source {
     const float* w;        // per-sample interp_weight (mode 2), else null
     float2* hspec;         // scratch: P*C*K half spectra of the RIR partitions, pre-scaled by 1/F
     float2* xspec;         // scratch: nb half spectra of the dry windows
+    struct RItem* items;   // scratch: this source's render work items (render_ctas() of them)
     int N, P, C, L;
     int K;                 // RIR partitions = ceil(L / kB)
     int nb;                // output blocks = ceil(N / kB)
     int mode;              // 0 static, 1 moving (bounds), 2 moving (idx, w)
-    int pad_[3];
+    int pad_[1];
 };
 
-enum { MODE_STATIC = 0, MODE_MOVING_BOUNDS = 1, MODE_MOVING_INDEXED = 2 };
+// One unit of k_render work: output block b of channel c (static: channels c, c+1), written by
+// k_prepare so that k_render never searches trajectories or prefix tables.
+struct RItem {
+    const float2* X;       // dry spectrum of block b
+    const float2* H0;      // RIR spectrum of (position 0, channel c, partition 0); position p at H0 + p * pstride
+    float* row;            // output row of channel c
+    int pstride;           // float2 words between positions (moving: C*K*kSpec) / to channel c+1 (static: K*kSpec)
+    int si, b, c;
+    int p_lo, p_hi;        // transforms p = p_lo, p_lo + 2, ... <= p_hi   (static: 0, 0)
+    int flags;             // bit 0: static source; bit 1: (static) channel c+1 exists
+    int pad_[2];
+};
+static_assert(sizeof(RItem) == 64, "RItem must be 64 bytes (copied as 4 x 16 B)");
+
+// One inverse transform, published by the CTA's thread 0 to the other threads through shared memory.
+struct XDesc {
+    const float2* X;       // global pointers, used for RIR partitions >= 1 (partition 0 is staged by TMA)
+    const float2* Hp;
+    const float2* Hq;      // null: only one filter packed into this transform
+    float* row;
+    int si, b, c, p;
+    int first;             // first transform of its block: plain store, otherwise read-add-store
+    int valid;
+    int p_lo;              // first position of the block (start of the per-thread segment walk)
+    int pad_;
+};
+static_assert(sizeof(XDesc) == 56 || sizeof(XDesc) == 64, "XDesc layout");
+
+SS_HD int range_ctas(const Source& s) { return (s.nb + 7) >> 3; }       // k_prepare: one warp per block
+
+// fill the work items of block b once its position range is known
+SS_HD void fill_items(const Source& s, int si, int b, int p_lo, int p_hi, int lane, int nlanes) {
+    if (s.mode == MODE_STATIC) {
+        const int ncp = (s.C + 1) >> 1;
+        for (int cp = lane; cp < ncp; cp += nlanes) {
+            RItem it;
+            it.X = s.xspec + (size_t)b * kSpec;
+            it.H0 = s.hspec + (size_t)(2 * cp) * s.K * kSpec;
+            it.row = s.out + (size_t)(2 * cp) * s.N;
+            it.pstride = s.K * kSpec;
+            it.si = si; it.b = b; it.c = 2 * cp; it.p_lo = 0; it.p_hi = 0;
+            it.flags = 1 | ((2 * cp + 1 < s.C) ? 2 : 0);
+            it.pad_[0] = 0; it.pad_[1] = 0;
+            s.items[(size_t)b * ncp + cp] = it;
+        }
+    } else {
+        for (int c = lane; c < s.C; c += nlanes) {
+            RItem it;
+            it.X = s.xspec + (size_t)b * kSpec;
+            it.H0 = s.hspec + (size_t)c * s.K * kSpec;
+            it.row = s.out + (size_t)c * s.N;
+            it.pstride = s.C * s.K * kSpec;
+            it.si = si; it.b = b; it.c = c; it.p_lo = p_lo; it.p_hi = p_hi;
+            it.flags = 0;
+            it.pad_[0] = 0; it.pad_[1] = 0;
+            s.items[(size_t)b * s.C + c] = it;
+        }
+    }
+}
+
+// transform (item, p) -> descriptor
+SS_HD XDesc make_xdesc(const RItem& it, int p) {
+    XDesc d;
+    d.X = it.X;
+    d.Hp = it.H0 + (size_t)p * it.pstride;
+    const bool has_q = (it.flags & 1) ? ((it.flags & 2) != 0) : (p + 1 <= it.p_hi);
+    d.Hq = has_q ? d.Hp + it.pstride : nullptr;
+    d.row = it.row;
+    d.si = it.si; d.b = it.b; d.c = it.c; d.p = p;
+    d.first = (p == it.p_lo);
+    d.valid = 1;
+    d.p_lo = it.p_lo;
+    d.pad_ = 0;
+    return d;
+}
 
 SS_HD int spectra_pairs_h(const Source& s) { return (s.P * s.C * s.K + 1) >> 1; }
 SS_HD int spectra_pairs_x(const Source& s) { return (s.nb + 1) >> 1; }
@@ -156,36 +233,51 @@ SS_HD void spectra_phase4(int t, const float2* s, const Row& ra, const Row& rb) 
 // one channel pair (static).
 // =======================================================================================
 
-// Z formation fused with pass A.  Hp / Hq: first partition's half spectrum of the two real
-// filters packed into this transform (Hq may be null).  X0 = xspec + b * kSpec; partition `part`
-// pairs with the dry window b - part.
-SS_HD void form_z(int t, const float2* X0, int b, int K, const float2* Hp, const float2* Hq, Regs32& R) {
+// Z formation fused with pass A.  sX / sHp / sHq: partition 0 of the dry window and of the two
+// real filters packed into this transform, staged in shared memory (linear, 4096 words each) by the
+// bulk-copy engine; sHq may be null.  RIR partitions j >= 1 (long RIRs) pair with dry window b - j
+// and are streamed from global memory through the pointers in `d`.
+SS_HD void form_z(int t, const float2* sX, const float2* sHp, const float2* sHq, const XDesc& d, int K, Regs32& R) {
     const int jB = passA_jB(t);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { R.a[i] = make_float2(0.f, 0.f); R.b[i] = make_float2(0.f, 0.f); }
-    const int kparts = (b + 1 < K) ? b + 1 : K;
-    for (int part = 0; part < kparts; ++part) {
-        const float2* xa_p = X0 - (size_t)part * kSpec + t;
-        const float2* xb_p = X0 - (size_t)part * kSpec + jB;
-        const float2* ha_p = Hp + (size_t)part * kSpec + t;
-        const float2* hb_p = Hp + (size_t)part * kSpec + jB;
-        if (Hq) {
-            const float2* ga_p = Hq + (size_t)part * kSpec + t;
-            const float2* gb_p = Hq + (size_t)part * kSpec + jB;
+    {
+        const float2 *xa_p = sX + t, *xb_p = sX + jB, *ha_p = sHp + t, *hb_p = sHp + jB;
+        if (sHq) {
+            const float2 *ga_p = sHq + t, *gb_p = sHq + jB;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
-                cmac(R.a[m], xa, ldg_stream(ha_p + 512 * m));            // P_A[m]
-                cmac(R.b[m], xb, ldg_stream(hb_p + 512 * m));            // P_B[m]
-                cmac(R.b[15 - m], xa, ldg_stream(ga_p + 512 * m));       // Q_A[m]
-                cmac(R.a[15 - m], xb, ldg_stream(gb_p + 512 * m));       // Q_B[m]
+                float2 xa = xa_p[512 * m], xb = xb_p[512 * m];
+                R.a[m] = cmul(xa, ha_p[512 * m]);            // P_A[m]
+                R.b[m] = cmul(xb, hb_p[512 * m]);            // P_B[m]
+                R.b[15 - m] = cmul(xa, ga_p[512 * m]);       // Q_A[m]
+                R.a[15 - m] = cmul(xb, gb_p[512 * m]);       // Q_B[m]
             }
         } else {
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
-                cmac(R.a[m], xa, ldg_stream(ha_p + 512 * m));
-                cmac(R.b[m], xb, ldg_stream(hb_p + 512 * m));
+                float2 xa = xa_p[512 * m], xb = xb_p[512 * m];
+                R.a[m] = cmul(xa, ha_p[512 * m]);
+                R.b[m] = cmul(xb, hb_p[512 * m]);
+                R.b[15 - m] = make_float2(0.f, 0.f);
+                R.a[15 - m] = make_float2(0.f, 0.f);
+            }
+        }
+    }
+    const int kparts = (d.b + 1 < K) ? d.b + 1 : K;
+    for (int part = 1; part < kparts; ++part) {
+        const float2* xa_p = d.X - (size_t)part * kSpec + t;
+        const float2* xb_p = d.X - (size_t)part * kSpec + jB;
+        const float2* ha_p = d.Hp + (size_t)part * kSpec + t;
+        const float2* hb_p = d.Hp + (size_t)part * kSpec + jB;
+        const float2* ga_p = d.Hq ? d.Hq + (size_t)part * kSpec + t : nullptr;
+        const float2* gb_p = d.Hq ? d.Hq + (size_t)part * kSpec + jB : nullptr;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
+            cmac(R.a[m], xa, ldg_stream(ha_p + 512 * m));
+            cmac(R.b[m], xb, ldg_stream(hb_p + 512 * m));
+            if (ga_p) {
+                cmac(R.b[15 - m], xa, ldg_stream(ga_p + 512 * m));
+                cmac(R.a[15 - m], xb, ldg_stream(gb_p + 512 * m));
             }
         }
     }
@@ -197,12 +289,14 @@ SS_HD void form_z(int t, const float2* X0, int b, int K, const float2* Hp, const
     }
     if (t == 0) {
         // thread 0 owns the self-mirrored butterflies 0 and 256 and the packed (DC, Nyquist) word
-        float pdc = 0.f, pny = 0.f, qdc = 0.f, qny = 0.f;
-        for (int part = 0; part < kparts; ++part) {
-            float2 x0 = (X0 - (size_t)part * kSpec)[0];
-            float2 h0 = (Hp + (size_t)part * kSpec)[0];
+        float2 x0 = sX[0], h0 = sHp[0];
+        float pdc = x0.x * h0.x, pny = x0.y * h0.y, qdc = 0.f, qny = 0.f;
+        if (sHq) { float2 g0 = sHq[0]; qdc = x0.x * g0.x; qny = x0.y * g0.y; }
+        for (int part = 1; part < kparts; ++part) {
+            x0 = (d.X - (size_t)part * kSpec)[0];
+            h0 = (d.Hp + (size_t)part * kSpec)[0];
             pdc += x0.x * h0.x; pny += x0.y * h0.y;
-            if (Hq) { float2 g0 = (Hq + (size_t)part * kSpec)[0]; qdc += x0.x * g0.x; qny += x0.y * g0.y; }
+            if (d.Hq) { float2 g0 = (d.Hq + (size_t)part * kSpec)[0]; qdc += x0.x * g0.x; qny += x0.y * g0.y; }
         }
         float2 tmp[8];
 #pragma unroll

@@ -54,56 +54,95 @@ static void cta_spectra(const Source& S, int local, const Tables& T) {
     for (int t = 0; t < kThreads; ++t) spectra_phase4(t, s, ra, rb);
 }
 
-static void cta_render(const Source& S, int local, const Tables& T) {
-    std::vector<float2> smem(kPadF);
-    std::vector<Regs32> R(kThreads);
-    float2* s = smem.data();
-    const int mode = S.mode;
-    int b, c, p_lo = 0, p_hi = 0;
-    std::vector<int> sg0(kThreads, 0);
-    if (mode == MODE_STATIC) {
-        const int ncp = (S.C + 1) >> 1;
-        b = local / ncp; c = 2 * (local - b * ncp);
-    } else {
-        b = local / S.C; c = local - b * S.C;
-    }
-    const int n0 = b * kB;
-    if (mode == MODE_MOVING_BOUNDS) {
+// k_prepare's range CTAs: position range of every block + its work items
+static void prepare_ranges(const Source& S, int si) {
+    for (int b = 0; b < S.nb; ++b) {
+        const int n0 = b * kB;
         const int n_last = (n0 + kB < S.N ? n0 + kB : S.N) - 1;
-        p_lo = seg_of(S.bounds, S.P - 1, n0);
-        p_hi = seg_of(S.bounds, S.P - 1, n_last) + 1;
-        for (int t = 0; t < kThreads; ++t) sg0[t] = seg_of(S.bounds, S.P - 1, n0 + t < S.N ? n0 + t : S.N - 1);
-    } else if (mode == MODE_MOVING_INDEXED) {
-        int pmin = 0x7fffffff, pmax = -1;
-        for (int t = 0; t < kThreads; ++t) {
-            int a, bb;
-            idx_range(t, n0, S, a, bb);
-            pmin = a < pmin ? a : pmin; pmax = bb > pmax ? bb : pmax;
+        int p_lo = 0, p_hi = 0;
+        if (S.mode == MODE_MOVING_BOUNDS) {
+            p_lo = seg_of(S.bounds, S.P - 1, n0);
+            p_hi = seg_of(S.bounds, S.P - 1, n_last) + 1;
+        } else if (S.mode == MODE_MOVING_INDEXED) {
+            int pmin = 0x7fffffff, pmax = -1;
+            for (int n = n0; n <= n_last; ++n) { int v = S.idx[n]; pmin = v < pmin ? v : pmin; pmax = v > pmax ? v : pmax; }
+            p_lo = pmin < 0 ? 0 : pmin;
+            p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
         }
-        p_lo = pmin < 0 ? 0 : pmin;
-        p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
+        for (int lane = 0; lane < 32; ++lane) fill_items(S, si, b, p_lo, p_hi, lane, 32);
     }
-    const float2* X0 = S.xspec + (size_t)b * kSpec;
-    float* row = S.out + (size_t)c * S.N;
-    for (int p = p_lo; p <= p_hi; p += 2) {
-        const float2 *Hp, *Hq;
-        if (mode == MODE_STATIC) {
-            Hp = S.hspec + (size_t)c * S.K * kSpec;
-            Hq = (c + 1 < S.C) ? Hp + (size_t)S.K * kSpec : nullptr;
-        } else {
-            Hp = S.hspec + ((size_t)p * S.C + c) * S.K * kSpec;
-            Hq = (p + 1 <= p_hi) ? Hp + (size_t)S.C * S.K * kSpec : nullptr;
+}
+
+// One persistent k_render CTA (`cta` of `grid`): same control flow as the kernel; the bulk copies
+// are done at the point where thread 0 issues them, the mbarrier waits are no-ops.
+static void cta_render(const Source* srcs, const RItem* items, int n_items, int cta, int grid, const Tables& T) {
+    std::vector<float2> smem(kPadF + kSpec);
+    std::vector<Regs32> R(kThreads);
+    float2* const fftbuf = smem.data();
+    float2* const sX = fftbuf;
+    float2* const sHp = fftbuf + kSpec;
+    float2* const sHq = fftbuf + kPadF;
+    RItem s_item[2];
+    XDesc s_desc[2];
+    int it_cur = cta, slot = 0, p_cur = 0;
+    {
+        XDesc d; memset(&d, 0, sizeof(d));
+        if (it_cur < n_items) {
+            s_item[0] = items[it_cur];
+            if (it_cur + grid < n_items) s_item[1] = items[it_cur + grid];
+            p_cur = s_item[0].p_lo;
+            d = make_xdesc(s_item[0], p_cur);
         }
-        for (int t = 0; t < kThreads; ++t) form_z(t, X0, b, S.K, Hp, Hq, R[t]);
-        for (int t = 0; t < kThreads; ++t) render_phase1(t, s, R[t]);
-        for (int t = 0; t < kThreads; ++t) load2(t, s, R[t]);
-        for (int t = 0; t < kThreads; ++t) passB2<true>(t, s, R[t], T);
+        s_desc[0] = d;
+        if (d.valid) {
+            memcpy(sX, d.X, sizeof(float2) * kSpec);
+            memcpy(sHp, d.Hp, sizeof(float2) * kSpec);
+            if (d.Hq) memcpy(sHq, d.Hq, sizeof(float2) * kSpec);
+        }
+    }
+    for (int k = 0;; ++k) {
+        const XDesc& d = s_desc[k & 1];
+        if (!d.valid) break;
+        const Source& S = srcs[d.si];
+        for (int t = 0; t < kThreads; ++t) form_z(t, sX, sHp, d.Hq ? sHq : nullptr, d, S.K, R[t]);
+        {   // thread 0: publish transform k+1, stage its Hq
+            XDesc nx; memset(&nx, 0, sizeof(nx));
+            const RItem& cur = s_item[slot];
+            if (p_cur + 2 <= cur.p_hi) { p_cur += 2; nx = make_xdesc(cur, p_cur); }
+            else if (it_cur + grid < n_items) {
+                it_cur += grid; slot ^= 1;
+                p_cur = s_item[slot].p_lo;
+                nx = make_xdesc(s_item[slot], p_cur);
+                if (it_cur + grid < n_items) s_item[slot ^ 1] = items[it_cur + grid];
+            }
+            s_desc[(k + 1) & 1] = nx;
+            if (nx.valid && nx.Hq) memcpy(sHq, nx.Hq, sizeof(float2) * kSpec);
+        }
+        for (int t = 0; t < kThreads; ++t) render_phase1(t, fftbuf, R[t]);
+        for (int t = 0; t < kThreads; ++t) load2(t, fftbuf, R[t]);
+        for (int t = 0; t < kThreads; ++t) passB2<true>(t, fftbuf, R[t], T);
+        for (int t = 0; t < kThreads; ++t) load2(t, fftbuf, R[t]);
+        const XDesc dcur = d;                      // (the device reads s_desc[k & 1] lazily; it is stable all iteration)
+        {   // thread 0: stage X, Hp of transform k+1 into the (now free) FFT buffer
+            const XDesc& nx = s_desc[(k + 1) & 1];
+            if (nx.valid) { memcpy(sX, nx.X, sizeof(float2) * kSpec); memcpy(sHp, nx.Hp, sizeof(float2) * kSpec); }
+        }
+        const int n0 = dcur.b * kB;
         for (int t = 0; t < kThreads; ++t) {
-            load2(t, s, R[t]);
             render_phase3(t, R[t], T);
-            if (mode == MODE_MOVING_BOUNDS) { MovingSinkBounds sk(S, row, n0, t, p, sg0[t], p == p_lo); render_epilogue(R[t], sk); }
-            else if (mode == MODE_MOVING_INDEXED) { MovingSinkIndexed sk(S, row, n0, t, p, p == p_lo); render_epilogue(R[t], sk); }
-            else { StaticSink sk{row, (c + 1 < S.C) ? row + S.N : nullptr, S.N, n0 + t}; render_epilogue(R[t], sk); }
+            if (S.mode == MODE_MOVING_BOUNDS) {
+                const int nn = n0 + t < S.N ? n0 + t : S.N - 1;
+                int sg0 = dcur.p_lo;
+                while (S.bounds[sg0 + 1] <= nn) ++sg0;
+                MovingSinkBounds sk(S, dcur.row, n0, t, dcur.p, sg0, dcur.first != 0);
+                render_epilogue(R[t], sk);
+            } else if (S.mode == MODE_MOVING_INDEXED) {
+                MovingSinkIndexed sk(S, dcur.row, n0, t, dcur.p, dcur.first != 0);
+                render_epilogue(R[t], sk);
+            } else {
+                StaticSink sk{dcur.row, dcur.Hq ? dcur.row + S.N : nullptr, S.N, n0 + t};
+                render_epilogue(R[t], sk);
+            }
         }
     }
 }
@@ -119,11 +158,14 @@ int emu_render(const float* x, const float* rir, float* out, const int32_t* boun
     S.x = x; S.rir = rir; S.out = out; S.bounds = bounds; S.idx = idx; S.w = w;
     S.N = N; S.P = P; S.C = C; S.L = L; S.K = (L + kB - 1) / kB; S.nb = (N + kB - 1) / kB; S.mode = mode;
     std::vector<float2> hs((size_t)P * C * S.K * kSpec), xs((size_t)S.nb * kSpec);
-    S.hspec = hs.data(); S.xspec = xs.data();
+    const int nr = render_ctas(S);
+    std::vector<RItem> items(nr);
+    S.hspec = hs.data(); S.xspec = xs.data(); S.items = items.data();
     const int ns = spectra_pairs_h(S) + spectra_pairs_x(S);
     for (int i = 0; i < ns; ++i) cta_spectra(S, i, T);
-    const int nr = render_ctas(S);
-    for (int i = 0; i < nr; ++i) cta_render(S, i, T);
+    prepare_ranges(S, 0);
+    const int grid = nr < 3 ? nr : 3;              // a few persistent CTAs, each looping over many items
+    for (int cta = 0; cta < grid; ++cta) cta_render(&S, items.data(), nr, cta, grid, T);
     return 0;
 }
 
