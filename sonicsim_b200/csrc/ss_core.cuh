@@ -60,6 +60,17 @@ SS_HD float2 ldg_cached(const float2* p) {
 #endif
 }
 
+// Fire-and-forget accumulate into global memory (second transform of a block that straddles a
+// waypoint).  Exactly two addends ever meet at an address and the first was stored by the same
+// thread earlier, so the result is order-independent (a + b == b + a in IEEE arithmetic).
+SS_HD void red_add(float* p, float v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+#else
+    *p += v;
+#endif
+}
+
 // Twiddle tables (forward sign, filled in double precision on the host):
 //   tw [m]           = exp(-2 pi i m / 8192)            m < 8192   (closing radix-2)
 //   twB[r * 16 + k]  = exp(-2 pi i k r / 256)           r, k < 16  (pass B)

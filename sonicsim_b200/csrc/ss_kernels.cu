@@ -115,6 +115,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// 64-byte work item, global -> shared, asynchronously (consumed one transform later)
+__device__ __forceinline__ void item_prefetch(RItem* dst, const RItem* src) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32((const char*)dst + 16 * i)), "l"((const char*)src + 16 * i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void item_prefetch_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int kSpecBytes = kSpec * (int)sizeof(float2);                       // 32 KB
@@ -152,7 +160,7 @@ k_render(const Source* __restrict__ srcs, const RItem* __restrict__ items, int n
         XDesc d; d.valid = 0;
         if (it_cur < n_items) {
             s_item[0] = items[it_cur];
-            if (it_cur + (int)gridDim.x < n_items) s_item[1] = items[it_cur + gridDim.x];
+            if (it_cur + (int)gridDim.x < n_items) item_prefetch(&s_item[1], &items[it_cur + gridDim.x]);
             p_cur = s_item[0].p_lo;
             d = make_xdesc(s_item[0], p_cur);
         }
@@ -184,9 +192,10 @@ k_render(const Source* __restrict__ srcs, const RItem* __restrict__ items, int n
             if (p_cur + 2 <= cur.p_hi) { p_cur += 2; nx = make_xdesc(cur, p_cur); }
             else if (it_cur + (int)gridDim.x < n_items) {
                 it_cur += gridDim.x; slot ^= 1;
+                item_prefetch_wait();                 // issued one item ago
                 p_cur = s_item[slot].p_lo;
                 nx = make_xdesc(s_item[slot], p_cur);
-                if (it_cur + (int)gridDim.x < n_items) s_item[slot ^ 1] = items[it_cur + gridDim.x];   // look-ahead load
+                if (it_cur + (int)gridDim.x < n_items) item_prefetch(&s_item[slot ^ 1], &items[it_cur + gridDim.x]);
             }
             s_desc[(k + 1) & 1] = nx;
             fence_proxy_async();

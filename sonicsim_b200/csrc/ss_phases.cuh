@@ -361,8 +361,7 @@ struct MovingSinkBounds {       // compact trajectory (MODE_MOVING_BOUNDS)
         float fa, fb;
         hat_pair(sg, w, p, fa, fb);
         float v = fa * z.x + fb * z.y;
-        if (!first) v += row[n];
-        row[n] = v;
+        if (first) row[n] = v; else red_add(row + n, v);
     }
 };
 struct MovingSinkIndexed {      // per-sample arrays (MODE_MOVING_INDEXED)
@@ -375,8 +374,7 @@ struct MovingSinkIndexed {      // per-sample arrays (MODE_MOVING_INDEXED)
         float fa, fb;
         hat_pair(idx[n], w[n], p, fa, fb);
         float v = fa * z.x + fb * z.y;
-        if (!first) v += row[n];
-        row[n] = v;
+        if (first) row[n] = v; else red_add(row + n, v);
     }
 };
 struct StaticSink {             // Re -> channel c0, Im -> channel c1 (row1 null if C is odd)
