@@ -130,6 +130,27 @@ typedef struct {
 /* ss_render_host + optional loudness normalisation of each stem while it is still in HBM. */
 int ss_render_host_ex(ss_ctx* ctx, const ss_source* items, int n_items, const ss_post_lufs* post);
 
+/* ---- mixture assembly of the training dataloader: separation/look2hear/datas/movingdatamodule.py
+ * :29-32 (compute_mch_rms_dB) and :105-124 (SIR gains of the interferers, SNR gain of the summed noise,
+ * both clamped at +40 dB, sums).  E = elements per stem (channels * samples). */
+typedef struct {
+    const float* speakers;    /* (S, E)  speaker_wav, speaker 0 is the reference                         */
+    const float* noises;      /* (M, E)  noise_wav                                                        */
+    const float* sirs;        /* (S - 1) SIR of each interferer in dB (reference: U(-6, 6))              */
+    float* mix;               /* (E)     mix_wav                                                          */
+    float* speakers_out;      /* (S, E)  speakers after their gains (may alias speakers; NULL = skip)    */
+    double* scratch;          /* ss_mix_scratch_doubles() doubles                                        */
+    int64_t E;
+    int32_t S, M;
+    float snr;                /* dB (reference: U(10, 20))                                               */
+    int32_t reserved;
+} ss_mix_item;
+
+int64_t ss_mix_scratch_doubles(void);
+int ss_mix_dev(ss_ctx* ctx, const ss_mix_item* items, int n_items, void* stream);      /* device pointers, async */
+int ss_mix_host(ss_ctx* ctx, const float* speakers, const float* noises, const float* sirs, float snr,
+                float* mix, float* speakers_out, int32_t S, int32_t M, int64_t E);      /* host pointers */
+
 /* Counters since ss_create / ss_reset_stats: kernels launched and device time is NOT measured
  * here (bench.py uses CUDA events); this is the launch count bench.py reports as gpu_launches. */
 int64_t ss_launch_count(const ss_ctx* ctx);

@@ -106,6 +106,38 @@ def main():
     cases["n_cases"] = np.int64(4)
     np.savez_compressed(os.path.join(OUT, "fft_conv.npz"), **cases)
 
+    # ---- f1: mixture assembly - the reference's own lines 105-124 of the dataloader, exec'd verbatim
+    # (the module itself cannot be imported: it needs pytorch_lightning / dataset files)
+    import textwrap
+    import types
+    src = open("/root/reference/separation/look2hear/datas/movingdatamodule.py").read().splitlines()
+    assert src[28].startswith("def compute_mch_rms_dB") and src[104].strip() == "# Random SIR and SNR", (src[28], src[104])
+    ns = {"torch": torch, "np": np}
+    exec("\n".join(src[28:32]), ns)                                   # compute_mch_rms_dB, :29-32
+    body = textwrap.dedent("\n".join(src[104:124]))                   # :105-124 (through mix_wav = ...)
+    cases = {}
+    for k, (seed, S, M, C, T) in enumerate([(61, 2, 1, 1, 16000), (62, 3, 2, 2, 4000), (63, 2, 1, 6, 2000)]):
+        rng = np.random.default_rng(seed)
+        shape_s = (S, T) if C == 1 else (S, C, T)
+        shape_n = (M, T) if C == 1 else (M, C, T)
+        spk = (rng.standard_normal(shape_s) * rng.uniform(0.01, 0.3, (S,) + (1,) * (len(shape_s) - 1))).astype(np.float32)
+        noi = (rng.standard_normal(shape_n) * 0.05).astype(np.float32)
+        if k == 2:
+            spk[1] *= 1e-4                                           # interferer far below the target: +40 dB clamp
+        torch.manual_seed(seed)
+        sirs = torch.Tensor(S - 1).uniform_(-6, 6).numpy()           # the draws the exec'd lines will make
+        snr = torch.Tensor(1).uniform_(10, 20).numpy()
+        torch.manual_seed(seed)
+        env = dict(ns)
+        env.update(self=types.SimpleNamespace(num_spks=S), speaker_wav=torch.from_numpy(spk.copy()),
+                   noise_wav=torch.from_numpy(noi.copy()))
+        exec(body, env)
+        cases[f"spk{k}"], cases[f"noise{k}"], cases[f"sirs{k}"], cases[f"snr{k}"] = spk, noi, sirs, snr
+        cases[f"mix{k}"] = env["mix_wav"].numpy()
+        cases[f"spk_out{k}"] = env["speaker_wav"].numpy()
+    cases["n_cases"] = np.int64(3)
+    np.savez_compressed(os.path.join(OUT, "mix_stems.npz"), **cases)
+
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -223,6 +223,36 @@ def get_lufs_norm_audio(audio, sr=16000, lufs=-6):
     return lufs_norm(data=audio, sr=sr, norm=class_lufs)
 
 
+# --------------------------------------------------------------------------- f1: mixture assembly
+def compute_mch_rms_dB(mch_wav):
+    """separation/look2hear/datas/movingdatamodule.py:29-32 (torch tensor in)."""
+    import torch
+    mean_square = max(1e-20, torch.mean(mch_wav ** 2))
+    return 10 * np.log10(mean_square)
+
+
+def mix_stems(speaker_wav, noise_wav, sirs, snr):
+    """separation/look2hear/datas/movingdatamodule.py:105-124 with the random SIRs / SNR passed in
+    (the reference draws them with torch.Tensor(n).uniform_).  speaker_wav (S, ..., T), noise_wav
+    (M, ..., T) torch float32; returns (mix_wav, scaled speaker_wav)."""
+    import torch
+    speaker_wav = speaker_wav.clone()
+    num_spks = speaker_wav.shape[0]
+    target_refch_energy = compute_mch_rms_dB(speaker_wav[0])                       # :107
+    for i in range(num_spks - 1):                                                  # :109
+        sir = sirs[i]
+        intf_refch_energy = compute_mch_rms_dB(speaker_wav[i + 1])
+        gain = min(target_refch_energy - intf_refch_energy - sir, 40)              # :112
+        speaker_wav[i + 1] *= 10. ** (gain / 20.)                                  # :113
+    all_speech = torch.sum(speaker_wav, dim=0)                                     # :115
+    all_noise = torch.sum(noise_wav, dim=0)                                        # :116
+    target_refch_energy = compute_mch_rms_dB(all_speech)                           # :118
+    noise_refch_energy = compute_mch_rms_dB(all_noise)                             # :120
+    gain = min(target_refch_energy - noise_refch_energy - snr, 40)                 # :121
+    all_noise = all_noise * 10. ** (float(np.asarray(gain).reshape(-1)[0]) / 20.)  # :122
+    return all_speech + all_noise, speaker_wav                                     # :124
+
+
 # ------------------------------------------------------------------- synthetic inputs
 def synth_rirs(rng, P, C, L, sr=16000, t60=0.5):
     """decaying Gaussian noise, small random per-position delay, divided by the

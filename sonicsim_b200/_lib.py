@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libsonicsim_b200.so")
-SOURCES = ["ss_kernels.cu", "ss_loudness.cu"]
+SOURCES = ["ss_kernels.cu", "ss_loudness.cu", "ss_mix.cu"]
 HEADERS = ["ss_core.cuh", "ss_phases.cuh", "ss_loud.cuh", "ss_internal.h", os.path.join("..", "..", "include", "sonicsim_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -28,6 +28,14 @@ class SsLoudItem(ctypes.Structure):
                 ("result", ctypes.c_void_p), ("stride_n", ctypes.c_int64), ("stride_c", ctypes.c_int64),
                 ("N", ctypes.c_int32), ("C", ctypes.c_int32), ("n_e", ctypes.c_int32), ("n_blocks", ctypes.c_int32),
                 ("rate", ctypes.c_double), ("block_size", ctypes.c_double), ("target_lufs", ctypes.c_double)]
+
+
+class SsMixItem(ctypes.Structure):
+    """`ss_mix_item` of include/sonicsim_b200.h."""
+    _fields_ = [("speakers", ctypes.c_void_p), ("noises", ctypes.c_void_p), ("sirs", ctypes.c_void_p),
+                ("mix", ctypes.c_void_p), ("speakers_out", ctypes.c_void_p), ("scratch", ctypes.c_void_p),
+                ("E", ctypes.c_int64), ("S", ctypes.c_int32), ("M", ctypes.c_int32), ("snr", ctypes.c_float),
+                ("reserved", ctypes.c_int32)]
 
 
 class SsPostLufs(ctypes.Structure):
@@ -108,6 +116,9 @@ def load():
         lib.ss_loudness_dev.argtypes = [vp, ctypes.POINTER(SsLoudItem), ctypes.c_int, vp]
         lib.ss_lufs_norm_host.argtypes = [vp, vp, vp, i32, i32, i64, i64, dbl, dbl, dbl, vp, i32, vp, vp, i32,
                                           ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
+        lib.ss_mix_scratch_doubles.restype = i64
+        lib.ss_mix_dev.argtypes = [vp, ctypes.POINTER(SsMixItem), ctypes.c_int, vp]
+        lib.ss_mix_host.argtypes = [vp, vp, vp, vp, ctypes.c_float, vp, vp, i32, i32, i64]
         lib.ss_launch_count.argtypes = [vp]
         lib.ss_launch_count.restype = i64
         lib.ss_reset_stats.argtypes = [vp]
@@ -124,7 +135,7 @@ def load():
 
 EXPORTS = ["ss_version", "ss_strerror", "ss_last_cuda_error", "ss_create", "ss_destroy",
            "ss_set_chunk_bytes", "ss_render_dev", "ss_render_host", "ss_render_host_ex", "ss_convolve_fixed_receiver",
-           "ss_convolve_moving_receiver", "ss_loudness_dev", "ss_lufs_norm_host", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
+           "ss_convolve_moving_receiver", "ss_loudness_dev", "ss_lufs_norm_host", "ss_mix_scratch_doubles", "ss_mix_dev", "ss_mix_host", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
            "ss_host_free"]
 
 

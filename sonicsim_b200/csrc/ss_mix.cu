@@ -1,0 +1,214 @@
+// sonicsim_b200 :: ss_mix.cu - mixture assembly of the training dataloader
+// (separation/look2hear/datas/movingdatamodule.py:29-32,105-124): active-energy (RMS dB) of the
+// reference speaker, SIR gains of the interferers (clamped to +40 dB), sum, SNR gain of the summed
+// noise, sum.  Three streaming passes over stems that are already in HBM + one tiny gain kernel;
+// per-block partial sums are combined in a fixed order, so results are run-to-run deterministic.
+#include <math.h>
+#include <string.h>
+
+#include "ss_internal.h"
+
+namespace {
+
+constexpr int kMixBlocks = 64;        // partial sums per mixture
+constexpr int kMaxStems = 8;
+
+struct MixItem {
+    const float* spk;      // (S, E)
+    const float* noise;    // (M, E)
+    const float* sirs;     // (S - 1)
+    float* mix;            // (E)
+    float* spk_out;        // (S, E) scaled speakers (may alias spk)
+    double* scratch;       // kMixBlocks * (S + 2) partial sums, then S + 1 gains at the end
+    long long E;
+    int S, M;
+    float snr;
+    int pad_;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0;
+    if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+    return r;          // valid in thread 0
+}
+
+// pass 1: sum of squares of every speaker stem and of the summed noise
+__global__ void __launch_bounds__(256) k_mix_energy(const MixItem* __restrict__ items) {
+    __shared__ double sh[8];
+    const MixItem& it = items[blockIdx.y];
+    double acc[kMaxStems + 1];
+#pragma unroll
+    for (int i = 0; i <= kMaxStems; ++i) acc[i] = 0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < it.E; e += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int s = 0; s < kMaxStems; ++s) if (s < it.S) { float v = it.spk[(long long)s * it.E + e]; acc[s] += (double)(v * v); }
+        float n = 0.f;
+        for (int m = 0; m < it.M; ++m) n += it.noise[(long long)m * it.E + e];
+        acc[kMaxStems] += (double)(n * n);
+    }
+#pragma unroll
+    for (int s = 0; s <= kMaxStems; ++s) {
+        if (s < it.S || s == kMaxStems) {
+            double r = block_sum(acc[s], sh);
+            if (threadIdx.x == 0) it.scratch[(long long)blockIdx.x * (kMaxStems + 2) + s] = r;
+        }
+    }
+}
+
+__device__ double rms_db(double sum_sq, long long count) {
+    double ms = sum_sq / (double)count;               // torch.mean(x ** 2)
+    if (ms < 1e-20) ms = 1e-20;                       // max(1e-20, .)   movingdatamodule.py:31
+    return 10.0 * log10(ms);
+}
+
+// gains of the interferers: gain_i = min(E(spk0) - E(spk_i) - sir_i, 40) dB   (:108-113)
+__global__ void k_mix_gain(const MixItem* __restrict__ items, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const MixItem& it = items[i];
+    double tot[kMaxStems + 1];
+    for (int s = 0; s <= kMaxStems; ++s) tot[s] = 0;
+    for (int b = 0; b < kMixBlocks; ++b)
+        for (int s = 0; s <= kMaxStems; ++s) if (s < it.S || s == kMaxStems) tot[s] += it.scratch[(long long)b * (kMaxStems + 2) + s];
+    double* g = it.scratch + (long long)kMixBlocks * (kMaxStems + 2);
+    const double target = rms_db(tot[0], it.E);
+    g[0] = 1.0;
+    for (int s = 1; s < it.S; ++s) {
+        double gain = target - rms_db(tot[s], it.E) - (double)it.sirs[s - 1];
+        if (gain > 40.0) gain = 40.0;
+        g[s] = pow(10.0, gain / 20.0);
+    }
+    g[kMaxStems] = rms_db(tot[kMaxStems], it.E);      // noise energy (dB), consumed by k_mix_write
+}
+
+// pass 2: energy of all_speech = sum_i g_i spk_i
+__global__ void __launch_bounds__(256) k_mix_speech_energy(const MixItem* __restrict__ items) {
+    __shared__ double sh[8];
+    const MixItem& it = items[blockIdx.y];
+    const double* g = it.scratch + (long long)kMixBlocks * (kMaxStems + 2);
+    float gf[kMaxStems];
+#pragma unroll
+    for (int s = 0; s < kMaxStems; ++s) gf[s] = s < it.S ? (float)g[s] : 0.f;
+    double acc = 0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < it.E; e += (long long)gridDim.x * blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int s = 0; s < kMaxStems; ++s) if (s < it.S) v += it.spk[(long long)s * it.E + e] * gf[s];
+        acc += (double)(v * v);
+    }
+    double r = block_sum(acc, sh);
+    if (threadIdx.x == 0) it.scratch[(long long)blockIdx.x * (kMaxStems + 2) + kMaxStems + 1] = r;
+}
+
+// pass 3: noise gain (:118-121), mixture and scaled speakers (:123-124)
+__global__ void __launch_bounds__(256) k_mix_write(const MixItem* __restrict__ items) {
+    const MixItem& it = items[blockIdx.y];
+    const double* g = it.scratch + (long long)kMixBlocks * (kMaxStems + 2);
+    double tot = 0;
+    for (int b = 0; b < kMixBlocks; ++b) tot += it.scratch[(long long)b * (kMaxStems + 2) + kMaxStems + 1];
+    double gain = rms_db(tot, it.E) - g[kMaxStems] - (double)it.snr;
+    if (gain > 40.0) gain = 40.0;
+    const float gn = (float)pow(10.0, gain / 20.0);
+    float gf[kMaxStems];
+#pragma unroll
+    for (int s = 0; s < kMaxStems; ++s) gf[s] = s < it.S ? (float)g[s] : 0.f;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < it.E; e += (long long)gridDim.x * blockDim.x) {
+        float sp = 0.f;
+#pragma unroll
+        for (int s = 0; s < kMaxStems; ++s) if (s < it.S) {
+            float v = it.spk[(long long)s * it.E + e] * gf[s];
+            if (it.spk_out) it.spk_out[(long long)s * it.E + e] = v;
+            sp += v;
+        }
+        float n = 0.f;
+        for (int m = 0; m < it.M; ++m) n += it.noise[(long long)m * it.E + e];
+        it.mix[e] = sp + n * gn;
+    }
+}
+
+}  // namespace
+
+extern "C" int ss_mix_dev(ss_ctx* c, const ss_mix_item* items, int n_items, void* stream_) {
+    if (!c || (!items && n_items > 0) || n_items < 0) return SS_ERR_INVALID;
+    if (n_items == 0) return SS_OK;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    for (int i = 0; i < n_items; ++i) {
+        const ss_mix_item& a = items[i];
+        if (!a.speakers || !a.noises || !a.mix || !a.scratch || a.E <= 0 || a.S < 1 || a.M < 1) return SS_ERR_INVALID;
+        if (a.S > kMaxStems || a.M > kMaxStems) return SS_ERR_UNSUPPORTED;
+        if (a.S > 1 && !a.sirs) return SS_ERR_INVALID;
+    }
+    const size_t bytes = align_up(sizeof(MixItem) * n_items, 16);
+    const int slot = c->ring_pos; c->ring_pos = (c->ring_pos + 1) % ss_ctx::kRing;
+    CK(cudaEventSynchronize(c->desc_ev[slot]));
+    if (bytes > c->desc_cap[slot]) {
+        if (c->h_desc[slot]) CK(cudaFreeHost(c->h_desc[slot]));
+        if (c->d_desc[slot]) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->d_desc[slot])); }
+        c->h_desc[slot] = nullptr; c->d_desc[slot] = nullptr; c->desc_cap[slot] = 0;
+        size_t cap = align_up(bytes * 2, 4096);
+        CK(cudaHostAlloc((void**)&c->h_desc[slot], cap, cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&c->d_desc[slot], cap));
+        c->desc_cap[slot] = cap;
+    }
+    MixItem* h = (MixItem*)c->h_desc[slot];
+    for (int i = 0; i < n_items; ++i) {
+        const ss_mix_item& a = items[i];
+        MixItem m; memset(&m, 0, sizeof(m));
+        m.spk = a.speakers; m.noise = a.noises; m.sirs = a.sirs; m.mix = a.mix; m.spk_out = a.speakers_out;
+        m.scratch = a.scratch; m.E = a.E; m.S = a.S; m.M = a.M; m.snr = a.snr;
+        h[i] = m;
+    }
+    CK(cudaMemcpyAsync(c->d_desc[slot], c->h_desc[slot], bytes, cudaMemcpyHostToDevice, stream));
+    CK(cudaEventRecord(c->desc_ev[slot], stream));
+    const MixItem* d = (const MixItem*)c->d_desc[slot];
+    dim3 grid(kMixBlocks, n_items);
+    k_mix_energy<<<grid, 256, 0, stream>>>(d);
+    k_mix_gain<<<(n_items + 63) / 64, 64, 0, stream>>>(d, n_items);
+    k_mix_speech_energy<<<grid, 256, 0, stream>>>(d);
+    k_mix_write<<<grid, 256, 0, stream>>>(d);
+    CK(cudaGetLastError());
+    c->launches += 4;
+    return SS_OK;
+}
+
+extern "C" int64_t ss_mix_scratch_doubles(void) { return (int64_t)kMixBlocks * (kMaxStems + 2) + kMaxStems + 1; }
+
+extern "C" int ss_mix_host(ss_ctx* c, const float* speakers, const float* noises, const float* sirs, float snr,
+                           float* mix, float* speakers_out, int32_t S, int32_t M, int64_t E) {
+    if (!c || !speakers || !noises || !mix || S < 1 || M < 1 || E <= 0) return SS_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const size_t o_spk = 0, o_noise = align_up(4 * (size_t)S * E, 256), o_mix = o_noise + align_up(4 * (size_t)M * E, 256);
+    const size_t o_sir = o_mix + align_up(4 * (size_t)E, 256), o_scr = o_sir + 256;
+    const size_t total = o_scr + align_up(8 * (size_t)ss_mix_scratch_doubles(), 256);
+    ss_ctx::Slot& sl = c->slot[0];
+    cudaStream_t st = c->s_cmp;
+    CK(cudaStreamSynchronize(st));
+    if (total > sl.in_cap) {
+        CK(cudaDeviceSynchronize());
+        if (sl.d_in) CK(cudaFree(sl.d_in));
+        sl.d_in = nullptr; sl.in_cap = 0;
+        CK(cudaMalloc((void**)&sl.d_in, align_up(total, 1 << 20)));
+        sl.in_cap = align_up(total, 1 << 20);
+    }
+    char* b = sl.d_in;
+    CK(cudaMemcpyAsync(b + o_spk, speakers, 4 * (size_t)S * E, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b + o_noise, noises, 4 * (size_t)M * E, cudaMemcpyHostToDevice, st));
+    if (S > 1) CK(cudaMemcpyAsync(b + o_sir, sirs, 4 * (size_t)(S - 1), cudaMemcpyHostToDevice, st));
+    ss_mix_item it; memset(&it, 0, sizeof(it));
+    it.speakers = (const float*)(b + o_spk); it.noises = (const float*)(b + o_noise); it.sirs = (const float*)(b + o_sir);
+    it.mix = (float*)(b + o_mix); it.speakers_out = speakers_out ? (float*)(b + o_spk) : nullptr;
+    it.scratch = (double*)(b + o_scr); it.E = E; it.S = S; it.M = M; it.snr = snr;
+    int rc = ss_mix_dev(c, &it, 1, (void*)st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(mix, b + o_mix, 4 * (size_t)E, cudaMemcpyDeviceToHost, st));
+    if (speakers_out) CK(cudaMemcpyAsync(speakers_out, b + o_spk, 4 * (size_t)S * E, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SS_OK;
+}
