@@ -71,6 +71,24 @@ SS_HD void red_add(float* p, float v) {
 #endif
 }
 
+// (1 - w) * a + w * b with every product and the sum rounded separately, like NumPy evaluates
+// SonicSim_moving.py:94 (no FMA contraction), so both trajectory forms give identical bits.
+SS_HD float lerp_terms(float fa, float a, float fb, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(__fmul_rn(fa, a), __fmul_rn(fb, b));
+#else
+    volatile float pa = fa * a, pb = fb * b;
+    return pa + pb;
+#endif
+}
+SS_HD float one_minus(float w) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(1.0f, w);
+#else
+    return 1.0f - w;
+#endif
+}
+
 // Twiddle tables (forward sign, filled in double precision on the host):
 //   tw [m]           = exp(-2 pi i m / 8192)            m < 8192   (closing radix-2)
 //   twB[r * 16 + k]  = exp(-2 pi i k r / 256)           r, k < 16  (pass B)

@@ -336,8 +336,9 @@ SS_HD void render_epilogue(const Regs32& R, Sink& sink) {
 // hat functions of positions (p, p+1) at a sample that lies in segment sg with weight w:
 //   reference lerp (SonicSim_moving.py:94):  (1 - w) * conv[sg] + w * conv[sg + 1]
 SS_HD void hat_pair(int sg, float w, int p, float& fa, float& fb) {
-    fa = (sg == p) ? (1.0f - w) : ((sg + 1 == p) ? w : 0.f);
-    fb = (sg == p + 1) ? (1.0f - w) : ((sg == p) ? w : 0.f);
+    const float omw = one_minus(w);
+    fa = (sg == p) ? omw : ((sg + 1 == p) ? w : 0.f);
+    fb = (sg == p + 1) ? omw : ((sg == p) ? w : 0.f);
 }
 
 // Output row of one CTA.  `first` = this is the first transform of the block (plain store),
@@ -360,7 +361,7 @@ struct MovingSinkBounds {       // compact trajectory (MODE_MOVING_BOUNDS)
         float w = (float)((double)(n - b0) * step);      // == np.linspace(0, 1, num, False)[i] as float32
         float fa, fb;
         hat_pair(sg, w, p, fa, fb);
-        float v = fa * z.x + fb * z.y;
+        float v = lerp_terms(fa, z.x, fb, z.y);
         if (first) row[n] = v; else red_add(row + n, v);
     }
 };
@@ -373,7 +374,7 @@ struct MovingSinkIndexed {      // per-sample arrays (MODE_MOVING_INDEXED)
         if (n >= N) return;
         float fa, fb;
         hat_pair(idx[n], w[n], p, fa, fb);
-        float v = fa * z.x + fb * z.y;
+        float v = lerp_terms(fa, z.x, fb, z.y);
         if (first) row[n] = v; else red_add(row + n, v);
     }
 };
