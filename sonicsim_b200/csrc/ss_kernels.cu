@@ -30,14 +30,69 @@ __device__ float2 g_tw[kF];          // exp(-2 pi i m / 8192)
 __device__ float2 g_twB[kTabB];      // [r][k] exp(-2 pi i k r / 256)
 __device__ float2 g_twC[kTabC];      // [r][k] exp(-2 pi i k r / 4096)
 
+// ----------------------------------------------------------------------------- k_blocks
+// One small CTA per chunk: block table of every source (one warp per source), 1 / n_s table, then the
+// exclusive scan that packs the render work items of all sources into one dense table.
+__global__ void __launch_bounds__(256)
+k_blocks(const Source* __restrict__ srcs, int n_src, int* __restrict__ total_items) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int si = warp; si < n_src; si += nwarps) {
+        const Source& S = srcs[si];
+        int nblk;
+        if (S.aligned) {
+            int carry = 0;
+            for (int base = 0; base < S.P - 1; base += 32) {
+                const int sg = base + lane;
+                const int b0 = sg < S.P - 1 ? S.bounds[sg] : 0;
+                const int n_s = sg < S.P - 1 ? S.bounds[sg + 1] - b0 : 0;
+                const int cnt = seg_blocks(n_s);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                const int first = carry + incl - cnt;
+                for (int q = 0; q < cnt; ++q) {
+                    Block bk; bk.start = b0 + kB * q; bk.len = n_s - kB * q < kB ? n_s - kB * q : kB; bk.p_lo = sg; bk.p_hi = sg + 1;
+                    S.blocks[first + q] = bk;
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            nblk = carry;
+        } else {
+            nblk = S.nb;
+            for (int bi = lane; bi < nblk; bi += 32) {
+                Block bk; bk.start = bi * kB; bk.len = S.N - bi * kB < kB ? S.N - bi * kB : kB; bk.p_lo = 0; bk.p_hi = 0;
+                S.blocks[bi] = bk;
+            }
+        }
+        for (int bi = nblk + lane; bi < S.nblk_max; bi += 32) { Block z; z.start = 0; z.len = 0; z.p_lo = 0; z.p_hi = 0; S.blocks[bi] = z; }
+        if (S.mode == MODE_MOVING_BOUNDS)
+            for (int sg = lane; sg < S.P - 1; sg += 32) S.rstep[sg] = 1.0 / (double)(S.bounds[sg + 1] - S.bounds[sg]);
+        if (lane == 0) S.counts[0] = nblk;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int carry = 0;
+        for (int base = 0; base < n_src; base += 32) {
+            const int si = base + lane;
+            const int cnt = si < n_src ? srcs[si].counts[0] * items_per_block(srcs[si]) : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (si < n_src) srcs[si].counts[1] = carry + incl - cnt;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) *total_items = carry;
+    }
+}
+
 // ----------------------------------------------------------------------------- k_prepare
 // CTA kinds, flattened per source through `prefix`:
 //   [0, nh)            two RIR-partition rows  -> two half spectra (one complex FFT)
 //   [nh, nh + nx)      two dry windows         -> two half spectra
-//   [nh + nx, ...)     8 output blocks each (one warp per block): position range of the block and
-//                      its k_render work items (RItem)
+//   [nh + nx, ...)     8 blocks each (one warp per block): position range of the block and its
+//                      k_render work items (RItem)
 __global__ void __launch_bounds__(kThreads, 2)
-k_prepare(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_src) {
+k_prepare(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_src, RItem* __restrict__ items) {
     extern __shared__ float2 smem[];
     const Tables T{g_tw, g_twB, g_twC};
     const int t = threadIdx.x;
@@ -47,31 +102,30 @@ k_prepare(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n
     Row ra, rb;
     const int nh = spectra_pairs_h(S), nx = spectra_pairs_x(S);
     if (local >= nh + nx) {
-        const int b = (local - nh - nx) * 8 + (t >> 5), lane = t & 31;
-        if (b >= S.nb) return;
-        const int n0 = b * kB;
-        const int n_last = (n0 + kB < S.N ? n0 + kB : S.N) - 1;
-        int p_lo = 0, p_hi = 0;
-        if (S.mode == MODE_MOVING_BOUNDS) {
-            p_lo = seg_of(S.bounds, S.P - 1, n0);
-            p_hi = seg_of(S.bounds, S.P - 1, n_last) + 1;
+        const int blk = (local - nh - nx) * 8 + (t >> 5), lane = t & 31;
+        if (blk >= S.counts[0]) return;
+        Block bk = S.blocks[blk];
+        if (S.mode == MODE_MOVING_BOUNDS && !S.aligned) {
+            bk.p_lo = seg_of(S.bounds, S.P - 1, bk.start);
+            bk.p_hi = seg_of(S.bounds, S.P - 1, bk.start + bk.len - 1) + 1;
         } else if (S.mode == MODE_MOVING_INDEXED) {
             int pmin = 0x7fffffff, pmax = -1;
-            for (int n = n0 + lane; n <= n_last; n += 32) { int v = S.idx[n]; pmin = v < pmin ? v : pmin; pmax = v > pmax ? v : pmax; }
+            for (int n = bk.start + lane; n < bk.start + bk.len; n += 32) { int v = S.idx[n]; pmin = v < pmin ? v : pmin; pmax = v > pmax ? v : pmax; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 int a = __shfl_xor_sync(0xffffffffu, pmin, o), bm = __shfl_xor_sync(0xffffffffu, pmax, o);
                 pmin = a < pmin ? a : pmin; pmax = bm > pmax ? bm : pmax;
             }
             // the reference raises IndexError for idx + 1 >= P (checked on the host path); clamp here
-            p_lo = pmin < 0 ? 0 : pmin;
-            p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
+            bk.p_lo = pmin < 0 ? 0 : pmin;
+            bk.p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
         }
-        fill_items(S, si, b, p_lo, p_hi, lane, 32);
+        fill_items(S, items, blk, bk, lane, 32);
         return;
     }
     if (local < nh) { ra = make_row_h(S, 2 * local); rb = make_row_h(S, 2 * local + 1); }
     else { local -= nh; ra = make_row_x(S, 2 * local); rb = make_row_x(S, 2 * local + 1); }
+    if (!ra.dst && !rb.dst) return;              // both block slots unused (aligned blocking over-allocates)
 
     Regs32 R;
     spectra_phase1(t, ra, rb, smem);
@@ -115,10 +169,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// 64-byte work item, global -> shared, asynchronously (consumed one transform later)
+// work item, global -> shared, asynchronously (consumed one transform later)
 __device__ __forceinline__ void item_prefetch(RItem* dst, const RItem* src) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < (int)sizeof(RItem) / 16; ++i)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32((const char*)dst + 16 * i)), "l"((const char*)src + 16 * i) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -136,7 +190,7 @@ constexpr int kRenderSmem = kPadF * (int)sizeof(float2) + kSpecBytes;         //
 // Hq into the staging buffer as soon as form_z(k) has consumed it, X and Hp into the FFT buffer itself
 // once pass C of transform k has read it out — so form_z never waits on L2.
 __global__ void __launch_bounds__(kThreads, SS_RENDER_MINB)
-k_render(const Source* __restrict__ srcs, const RItem* __restrict__ items, int n_items) {
+k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr) {
     extern __shared__ __align__(128) float2 smem[];
     __shared__ __align__(16) RItem s_item[2];
     __shared__ __align__(16) XDesc s_desc[2];
@@ -147,6 +201,7 @@ k_render(const Source* __restrict__ srcs, const RItem* __restrict__ items, int n
     float2* const sHq = smem + kPadF;
     const Tables T{g_tw, g_twB, g_twC};
     const int t = threadIdx.x;
+    const int n_items = *n_items_ptr;          // written by k_blocks (aligned blocking: known only on the device)
 
     // thread-0 iterator state
     int it_cur = blockIdx.x;          // item of the transform most recently published
@@ -157,7 +212,7 @@ k_render(const Source* __restrict__ srcs, const RItem* __restrict__ items, int n
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        XDesc d; d.valid = 0;
+        XDesc d; d.valid = 0; d.Hq = nullptr;
         if (it_cur < n_items) {
             s_item[0] = items[it_cur];
             if (it_cur + (int)gridDim.x < n_items) item_prefetch(&s_item[1], &items[it_cur + gridDim.x]);
@@ -182,12 +237,11 @@ k_render(const Source* __restrict__ srcs, const RItem* __restrict__ items, int n
         mbar_wait(&s_bar[1], k & 1);
         const XDesc& d = s_desc[k & 1];
         if (!d.valid) break;
-        const Source& S = srcs[d.si];
-        form_z(t, sX, sHp, d.Hq ? sHq : nullptr, d, S.K, R);
+        form_z(t, sX, sHp, d.Hq ? sHq : nullptr, d, R);
         __syncthreads();                              // staged spectra consumed, s_desc[k & 1] read by all
         if (t == 0) {
             // publish transform k+1 and start staging its Hq
-            XDesc nx; nx.valid = 0;
+            XDesc nx; nx.valid = 0; nx.Hq = nullptr;
             const RItem& cur = s_item[slot];
             if (p_cur + 2 <= cur.p_hi) { p_cur += 2; nx = make_xdesc(cur, p_cur); }
             else if (it_cur + (int)gridDim.x < n_items) {
@@ -220,20 +274,7 @@ k_render(const Source* __restrict__ srcs, const RItem* __restrict__ items, int n
             } else mbar_arrive(&s_bar[0]);
         }
         render_phase3(t, R, T);
-        const int n0 = d.b * kB;
-        if (S.mode == MODE_MOVING_BOUNDS) {
-            const int nn = n0 + t < S.N ? n0 + t : S.N - 1;
-            int sg0 = d.p_lo;
-            while (S.bounds[sg0 + 1] <= nn) ++sg0;
-            MovingSinkBounds sk(S, d.row, n0, t, d.p, sg0, d.first != 0);
-            render_epilogue(R, sk);
-        } else if (S.mode == MODE_MOVING_INDEXED) {
-            MovingSinkIndexed sk(S, d.row, n0, t, d.p, d.first != 0);
-            render_epilogue(R, sk);
-        } else {
-            StaticSink sk{d.row, d.Hq ? d.row + S.N : nullptr, S.N, n0 + t};
-            render_epilogue(R, sk);
-        }
+        render_epilogue(t, d, R);
     }
 }
 
@@ -366,16 +407,27 @@ static int validate_item(const ss_source& it) {
     else return SS_ERR_INVALID;
     return SS_OK;
 }
+// shapes derived from one ss_source
+struct Shape { int K, nb, aligned, nblk_max, per, max_items; };
+static Shape shape_of(const ss_source& it) {
+    Shape s;
+    s.K = (it.L + kB - 1) / kB; s.nb = (it.N + kB - 1) / kB;
+    s.aligned = (it.mode == SS_MOVING_BOUNDS && s.K == 1) ? 1 : 0;
+    s.nblk_max = s.aligned ? s.nb + it.P - 1 : s.nb;
+    s.per = it.mode == SS_STATIC ? (it.C + 1) / 2 : it.C;
+    s.max_items = s.nblk_max * s.per;
+    return s;
+}
 static size_t spectra_bytes(const ss_source& it) {
-    size_t K = (it.L + kB - 1) / kB, nb = (it.N + kB - 1) / kB;
-    size_t n_items = it.mode == SS_STATIC ? nb * ((it.C + 1) / 2) : nb * (size_t)it.C;
-    return ((size_t)it.P * it.C * K + nb) * kSpec * sizeof(float2) + n_items * sizeof(RItem);
+    const Shape sh = shape_of(it);
+    return ((size_t)it.P * it.C * sh.K + sh.nblk_max) * kSpec * sizeof(float2) + (size_t)sh.max_items * sizeof(RItem) +
+           align_up(sizeof(Block) * (size_t)sh.nblk_max, 256) + align_up(sizeof(double) * (size_t)it.P, 256) + 256;
 }
 
 // Enqueue the three launches for items[first, last) (device pointers) on `stream`.
 static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, cudaStream_t stream) {
     const int n = last - first;
-    size_t need = 0;
+    size_t need = 256;
     for (int i = first; i < last; ++i) need += spectra_bytes(items[i]);
     if (need > c->scratch_cap) {
         CK(cudaDeviceSynchronize());
@@ -385,10 +437,9 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
         CK(cudaMalloc(&c->d_scratch, cap));
         c->scratch_cap = cap;
     }
-    // descriptor block: Source[n] | prefix_spec[n+1] | prefix_render[n+1]
+    // descriptor block: Source[n] | prefix_prepare[n+1]
     const size_t off_ps = align_up(sizeof(Source) * n, 16);
-    const size_t off_pr = off_ps + align_up(sizeof(int) * (n + 1), 16);
-    const size_t bytes = off_pr + align_up(sizeof(int) * (n + 1), 16);
+    const size_t bytes = off_ps + align_up(sizeof(int) * (n + 1), 16);
     const int slot = c->ring_pos; c->ring_pos = (c->ring_pos + 1) % ss_ctx::kRing;
     if (bytes > c->desc_cap[slot]) {
         CK(cudaEventSynchronize(c->desc_ev[slot]));
@@ -404,11 +455,11 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
     }
     Source* hs = (Source*)c->h_desc[slot];
     int* hps = (int*)(c->h_desc[slot] + off_ps);
-    int* hpr = (int*)(c->h_desc[slot] + off_pr);
     char* scratch = c->d_scratch;
     int ps = 0, pr = 0;
     for (int i = 0; i < n; ++i) {
         const ss_source& it = items[first + i];
+        const Shape sh = shape_of(it);
         Source s;
         memset(&s, 0, sizeof(s));
         s.x = it.x; s.rir = it.rir; s.out = it.out;
@@ -416,37 +467,40 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
         s.idx = it.mode == SS_MOVING_INDEXED ? it.idx : nullptr;
         s.w = it.mode == SS_MOVING_INDEXED ? it.w : nullptr;
         s.N = it.N; s.P = it.P; s.C = it.C; s.L = it.L;
-        s.K = (it.L + kB - 1) / kB; s.nb = (it.N + kB - 1) / kB;
-        s.mode = it.mode;
+        s.K = sh.K; s.nb = sh.nb; s.mode = it.mode; s.aligned = sh.aligned; s.nblk_max = sh.nblk_max;
         s.hspec = (float2*)scratch; scratch += (size_t)s.P * s.C * s.K * kSpec * sizeof(float2);
-        s.xspec = (float2*)scratch; scratch += (size_t)s.nb * kSpec * sizeof(float2);
+        s.xspec = (float2*)scratch; scratch += (size_t)s.nblk_max * kSpec * sizeof(float2);
+        s.blocks = (Block*)scratch; scratch += align_up(sizeof(Block) * (size_t)s.nblk_max, 256);
+        s.rstep = (double*)scratch; scratch += align_up(sizeof(double) * (size_t)s.P, 256);
+        s.counts = (int*)scratch; scratch += 256;
         hs[i] = s;
-        hps[i] = ps; hpr[i] = pr;
+        hps[i] = ps;
         ps += spectra_pairs_h(s) + spectra_pairs_x(s) + range_ctas(s);
-        pr += render_ctas(s);
+        pr += sh.max_items;
     }
-    // work-item table of the whole chunk, contiguous in source order, after all spectra
-    RItem* d_items = (RItem*)scratch;
-    for (int i = 0; i < n; ++i) hs[i].items = d_items + hpr[i];
-    hps[n] = ps; hpr[n] = pr;
+    hps[n] = ps;
+    // work-item table of the whole chunk (dense, filled through the k_blocks scan) + its length
+    RItem* d_items = (RItem*)scratch; scratch += (size_t)pr * sizeof(RItem);
+    int* d_total = (int*)scratch;
     CK(cudaMemcpyAsync(c->d_desc[slot], c->h_desc[slot], bytes, cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(c->desc_ev[slot], stream));
     const Source* ds = (const Source*)c->d_desc[slot];
     const int* dps = (const int*)(c->d_desc[slot] + off_ps);
-    const int* dpr = (const int*)(c->d_desc[slot] + off_pr);
     ss_ctx::Prof pf;
     if (c->profiling) {
         CK(cudaEventCreate(&pf.e0)); CK(cudaEventCreate(&pf.e1)); CK(cudaEventCreate(&pf.e2));
         CK(cudaEventRecord(pf.e0, stream));
     }
-    k_prepare<<<ps, kThreads, kPadF * (int)sizeof(float2), stream>>>(ds, dps, n);
+    k_blocks<<<1, 256, 0, stream>>>(ds, n, d_total);
+    CK(cudaGetLastError());
+    k_prepare<<<ps, kThreads, kPadF * (int)sizeof(float2), stream>>>(ds, dps, n, d_items);
     CK(cudaGetLastError());
     if (c->profiling) CK(cudaEventRecord(pf.e1, stream));
     const int grid_r = pr < c->sm_count * SS_RENDER_MINB ? pr : c->sm_count * SS_RENDER_MINB;
-    k_render<<<grid_r, kThreads, kRenderSmem, stream>>>(ds, d_items, pr);
+    k_render<<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total);
     CK(cudaGetLastError());
     if (c->profiling) { CK(cudaEventRecord(pf.e2, stream)); c->prof.push_back(pf); }
-    c->launches += 2;
+    c->launches += 3;
     return SS_OK;
 }
 

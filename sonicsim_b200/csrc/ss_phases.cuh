@@ -11,6 +11,16 @@ namespace ss {
 
 enum { MODE_STATIC = 0, MODE_MOVING_BOUNDS = 1, MODE_MOVING_INDEXED = 2 };
 
+// One output block: samples [start, start + len), len <= 4096, rendered by one transform per pair of
+// positions in [p_lo, p_hi].  len == 0: unused slot of the table.
+//   grid blocking     start = 4096 b                     (long RIRs, indexed trajectories, static sources)
+//   aligned blocking  blocks never cross a waypoint: every block lies in one segment s and needs
+//                     exactly the pair (s, s + 1) -> one transform, both packed results used
+//                     (bounds trajectory and L <= 4096)
+struct Block { int start, len, p_lo, p_hi; };
+
+struct RItem;
+
 // One (utterance, source) unit.  Reference shapes: dry (N,), RIRs (P, C, L), output (C, N)
 // (SonicSim_moving.py:63-96); static source has P = 1 (SonicSim_moving.py:47-61).
 struct Source {
@@ -21,28 +31,38 @@ struct Source {
     const int* idx;        // per-sample interp_index  (mode 2), else null
     const float* w;        // per-sample interp_weight (mode 2), else null
     float2* hspec;         // scratch: P*C*K half spectra of the RIR partitions, pre-scaled by 1/F
-    float2* xspec;         // scratch: nb half spectra of the dry windows
-    struct RItem* items;   // scratch: this source's render work items (render_ctas() of them)
+    float2* xspec;         // scratch: nblk_max half spectra of the dry windows
+    Block* blocks;         // scratch: nblk_max blocks (k_blocks)
+    double* rstep;         // scratch: 1 / (samples in segment s), s < P - 1 (mode 1)
+    int* counts;           // scratch: [0] = blocks in use, [1] = index of this source's first render item
     int N, P, C, L;
     int K;                 // RIR partitions = ceil(L / kB)
-    int nb;                // output blocks = ceil(N / kB)
+    int nb;                // ceil(N / kB)
     int mode;              // 0 static, 1 moving (bounds), 2 moving (idx, w)
-    int pad_[1];
+    int aligned;           // 1: blocks aligned to the trajectory segments (mode 1 and K == 1)
+    int nblk_max;          // table size: nb (grid) or nb + P - 1 (aligned)
+    int pad_[3];
 };
 
-// One unit of k_render work: output block b of channel c (static: channels c, c+1), written by
-// k_prepare so that k_render never searches trajectories or prefix tables.
+// One unit of k_render work: one block of channel c (static: channels c, c+1), written by k_prepare
+// so that k_render never searches trajectories, prefix tables or the Source array.
 struct RItem {
-    const float2* X;       // dry spectrum of block b
+    const float2* X;       // dry spectrum of the block's window [start - 4096, start + 4096)
     const float2* H0;      // RIR spectrum of (position 0, channel c, partition 0); position p at H0 + p * pstride
     float* row;            // output row of channel c
+    float* row1;           // static source: output row of channel c + 1, or null
+    const int* bounds;     // trajectory of the source (mode 1)
+    const double* rstep;   //   "
+    const int* idx;        // (mode 2)
+    const float* w;        // (mode 2)
     int pstride;           // float2 words between positions (moving: C*K*kSpec) / to channel c+1 (static: K*kSpec)
-    int si, b, c;
+    int n0, n_end;         // output samples [n0, n_end)
     int p_lo, p_hi;        // transforms p = p_lo, p_lo + 2, ... <= p_hi   (static: 0, 0)
-    int flags;             // bit 0: static source; bit 1: (static) channel c+1 exists
-    int pad_[2];
+    int mode;
+    int kparts;            // RIR partitions that reach back into the signal: min(K, n0 / 4096 + 1)
+    int pad_[5];
 };
-static_assert(sizeof(RItem) == 64, "RItem must be 64 bytes (copied as 4 x 16 B)");
+static_assert(sizeof(RItem) == 112, "RItem is copied as 7 x 16 B");
 
 // One inverse transform, published by the CTA's thread 0 to the other threads through shared memory.
 struct XDesc {
@@ -50,42 +70,58 @@ struct XDesc {
     const float2* Hp;
     const float2* Hq;      // null: only one filter packed into this transform
     float* row;
-    int si, b, c, p;
-    int first;             // first transform of its block: plain store, otherwise read-add-store
+    float* row1;
+    const int* bounds;
+    const double* rstep;
+    const int* idx;
+    const float* w;
+    int n0, n_end, p, p_lo;
+    int first;             // first transform of its block: plain store, otherwise accumulate
     int valid;
-    int p_lo;              // first position of the block (start of the per-thread segment walk)
-    int pad_;
+    int mode;
+    int kparts;
 };
-static_assert(sizeof(XDesc) == 56 || sizeof(XDesc) == 64, "XDesc layout");
+static_assert(sizeof(XDesc) == 104, "XDesc layout");
 
-SS_HD int range_ctas(const Source& s) { return (s.nb + 7) >> 3; }       // k_prepare: one warp per block
+SS_HD int spectra_pairs_h(const Source& s) { return (s.P * s.C * s.K + 1) >> 1; }
+SS_HD int spectra_pairs_x(const Source& s) { return (s.nblk_max + 1) >> 1; }
+SS_HD int range_ctas(const Source& s) { return (s.nblk_max + 7) >> 3; }       // k_prepare: one warp per block
+SS_HD int items_per_block(const Source& s) { return s.mode == MODE_STATIC ? (s.C + 1) >> 1 : s.C; }
+SS_HD int max_render_items(const Source& s) { return s.nblk_max * items_per_block(s); }
 
-// fill the work items of block b once its position range is known
-SS_HD void fill_items(const Source& s, int si, int b, int p_lo, int p_hi, int lane, int nlanes) {
+// blocks of one segment under aligned blocking
+SS_HD int seg_blocks(int n_s) { return (n_s + kB - 1) / kB; }
+
+// fill the work items of block `blk` once its position range is known (lanes split the channels)
+SS_HD void fill_items(const Source& s, RItem* items, int blk, const Block& bk, int lane, int nlanes) {
+    RItem it;
+    it.X = s.xspec + (size_t)blk * kSpec;
+    it.bounds = s.bounds; it.rstep = s.rstep; it.idx = s.idx; it.w = s.w;
+    it.n0 = bk.start; it.n_end = bk.start + bk.len;
+    it.mode = s.mode;
+    const int reach = bk.start / kB + 1;
+    it.kparts = reach < s.K ? reach : s.K;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) it.pad_[i] = 0;
+    const int per = items_per_block(s);
+    RItem* dst = items + s.counts[1] + (size_t)blk * per;
     if (s.mode == MODE_STATIC) {
-        const int ncp = (s.C + 1) >> 1;
-        for (int cp = lane; cp < ncp; cp += nlanes) {
-            RItem it;
-            it.X = s.xspec + (size_t)b * kSpec;
+        for (int cp = lane; cp < per; cp += nlanes) {
             it.H0 = s.hspec + (size_t)(2 * cp) * s.K * kSpec;
             it.row = s.out + (size_t)(2 * cp) * s.N;
+            it.row1 = (2 * cp + 1 < s.C) ? it.row + s.N : nullptr;
             it.pstride = s.K * kSpec;
-            it.si = si; it.b = b; it.c = 2 * cp; it.p_lo = 0; it.p_hi = 0;
-            it.flags = 1 | ((2 * cp + 1 < s.C) ? 2 : 0);
-            it.pad_[0] = 0; it.pad_[1] = 0;
-            s.items[(size_t)b * ncp + cp] = it;
+            it.p_lo = 0; it.p_hi = 0;
+            dst[cp] = it;
         }
     } else {
-        for (int c = lane; c < s.C; c += nlanes) {
-            RItem it;
-            it.X = s.xspec + (size_t)b * kSpec;
+        for (int c = lane; c < per; c += nlanes) {
             it.H0 = s.hspec + (size_t)c * s.K * kSpec;
             it.row = s.out + (size_t)c * s.N;
+            it.row1 = nullptr;
             it.pstride = s.C * s.K * kSpec;
-            it.si = si; it.b = b; it.c = c; it.p_lo = p_lo; it.p_hi = p_hi;
-            it.flags = 0;
-            it.pad_[0] = 0; it.pad_[1] = 0;
-            s.items[(size_t)b * s.C + c] = it;
+            it.p_lo = bk.p_lo; it.p_hi = bk.p_hi;
+            dst[c] = it;
         }
     }
 }
@@ -95,21 +131,16 @@ SS_HD XDesc make_xdesc(const RItem& it, int p) {
     XDesc d;
     d.X = it.X;
     d.Hp = it.H0 + (size_t)p * it.pstride;
-    const bool has_q = (it.flags & 1) ? ((it.flags & 2) != 0) : (p + 1 <= it.p_hi);
+    const bool has_q = (it.mode == MODE_STATIC) ? (it.row1 != nullptr) : (p + 1 <= it.p_hi);
     d.Hq = has_q ? d.Hp + it.pstride : nullptr;
-    d.row = it.row;
-    d.si = it.si; d.b = it.b; d.c = it.c; d.p = p;
+    d.row = it.row; d.row1 = it.row1;
+    d.bounds = it.bounds; d.rstep = it.rstep; d.idx = it.idx; d.w = it.w;
+    d.n0 = it.n0; d.n_end = it.n_end; d.p = p; d.p_lo = it.p_lo;
     d.first = (p == it.p_lo);
     d.valid = 1;
-    d.p_lo = it.p_lo;
-    d.pad_ = 0;
+    d.mode = it.mode;
+    d.kparts = it.kparts;
     return d;
-}
-
-SS_HD int spectra_pairs_h(const Source& s) { return (s.P * s.C * s.K + 1) >> 1; }
-SS_HD int spectra_pairs_x(const Source& s) { return (s.nb + 1) >> 1; }
-SS_HD int render_ctas(const Source& s) {
-    return s.mode == MODE_STATIC ? s.nb * ((s.C + 1) >> 1) : s.nb * s.C;
 }
 
 // largest i with prefix[i] <= v, prefix[0] = 0, prefix has n+1 entries
@@ -145,10 +176,13 @@ SS_HD Row make_row_h(const Source& s, int row) {
 }
 SS_HD Row make_row_x(const Source& s, int blk) {
     Row r;
-    if (blk >= s.nb) { r.base = nullptr; r.dst = nullptr; r.g0 = 0; r.len = 0; r.ncap = 0; r.scale = 0.f; return r; }
+    r.base = nullptr; r.dst = nullptr; r.g0 = 0; r.len = 0; r.ncap = 0; r.scale = 0.f;
+    if (blk >= s.nblk_max) return r;
+    const Block bk = s.blocks[blk];
+    if (bk.len == 0) return r;
     r.base = s.x;
     r.dst = s.xspec + (size_t)blk * kSpec;
-    r.g0 = (blk - 1) * kB; r.len = s.N; r.ncap = kF;
+    r.g0 = bk.start - kB; r.len = s.N; r.ncap = kF;
     r.scale = 1.0f;
     return r;
 }
@@ -233,11 +267,37 @@ SS_HD void spectra_phase4(int t, const float2* s, const Row& ra, const Row& rb) 
 // one channel pair (static).
 // =======================================================================================
 
+// RIR partitions >= 1 (long RIRs only), streamed from global memory and accumulated into the
+// (P_A, P_B, Q_A, Q_B) slots of form_z.  Out of line on purpose: it keeps the K = 1 fast path small.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+inline void form_z_parts(int t, const XDesc& d, float2* Ra, float2* Rb) {
+    const int jB = passA_jB(t);
+    for (int part = 1; part < d.kparts; ++part) {
+        const float2* xa_p = d.X - (size_t)part * kSpec + t;
+        const float2* xb_p = d.X - (size_t)part * kSpec + jB;
+        const float2* ha_p = d.Hp + (size_t)part * kSpec + t;
+        const float2* hb_p = d.Hp + (size_t)part * kSpec + jB;
+        const float2* ga_p = d.Hq ? d.Hq + (size_t)part * kSpec + t : nullptr;
+        const float2* gb_p = d.Hq ? d.Hq + (size_t)part * kSpec + jB : nullptr;
+        for (int m = 0; m < 8; ++m) {
+            float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
+            cmac(Ra[m], xa, ldg_stream(ha_p + 512 * m));
+            cmac(Rb[m], xb, ldg_stream(hb_p + 512 * m));
+            if (ga_p) {
+                cmac(Rb[15 - m], xa, ldg_stream(ga_p + 512 * m));
+                cmac(Ra[15 - m], xb, ldg_stream(gb_p + 512 * m));
+            }
+        }
+    }
+}
+
 // Z formation fused with pass A.  sX / sHp / sHq: partition 0 of the dry window and of the two
 // real filters packed into this transform, staged in shared memory (linear, 4096 words each) by the
-// bulk-copy engine; sHq may be null.  RIR partitions j >= 1 (long RIRs) pair with dry window b - j
-// and are streamed from global memory through the pointers in `d`.
-SS_HD void form_z(int t, const float2* sX, const float2* sHp, const float2* sHq, const XDesc& d, int K, Regs32& R) {
+// bulk-copy engine; sHq may be null.  RIR partitions j >= 1 (long RIRs) pair with the dry window
+// 4096 j samples earlier (grid blocking) and are streamed from global memory through `d`.
+SS_HD void form_z(int t, const float2* sX, const float2* sHp, const float2* sHq, const XDesc& d, Regs32& R) {
     const int jB = passA_jB(t);
     {
         const float2 *xa_p = sX + t, *xb_p = sX + jB, *ha_p = sHp + t, *hb_p = sHp + jB;
@@ -262,24 +322,14 @@ SS_HD void form_z(int t, const float2* sX, const float2* sHp, const float2* sHq,
             }
         }
     }
-    const int kparts = (d.b + 1 < K) ? d.b + 1 : K;
-    for (int part = 1; part < kparts; ++part) {
-        const float2* xa_p = d.X - (size_t)part * kSpec + t;
-        const float2* xb_p = d.X - (size_t)part * kSpec + jB;
-        const float2* ha_p = d.Hp + (size_t)part * kSpec + t;
-        const float2* hb_p = d.Hp + (size_t)part * kSpec + jB;
-        const float2* ga_p = d.Hq ? d.Hq + (size_t)part * kSpec + t : nullptr;
-        const float2* gb_p = d.Hq ? d.Hq + (size_t)part * kSpec + jB : nullptr;
+    const int kparts = d.kparts;
+    if (kparts > 1) {
+        float2 ta[16], tb[16];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
-            cmac(R.a[m], xa, ldg_stream(ha_p + 512 * m));
-            cmac(R.b[m], xb, ldg_stream(hb_p + 512 * m));
-            if (ga_p) {
-                cmac(R.b[15 - m], xa, ldg_stream(ga_p + 512 * m));
-                cmac(R.a[15 - m], xb, ldg_stream(gb_p + 512 * m));
-            }
-        }
+        for (int i = 0; i < 16; ++i) { ta[i] = R.a[i]; tb[i] = R.b[i]; }
+        form_z_parts(t, d, ta, tb);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { R.a[i] = ta[i]; R.b[i] = tb[i]; }
     }
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
@@ -326,13 +376,6 @@ SS_HD void render_phase3(int t, Regs32& R, const Tables& T) {
         R.a[sl] = csub(R.a[sl], cmul(R.b[sl], final_twiddle<true>(t, r, wt)));
     }
 }
-// epilogue: the sink is called with r = 0..15 in order; it may carry state from sample to sample
-template <class Sink>
-SS_HD void render_epilogue(const Regs32& R, Sink& sink) {
-#pragma unroll
-    for (int r = 0; r < 16; ++r) sink(r, R.a[out16(r)]);
-}
-
 // hat functions of positions (p, p+1) at a sample that lies in segment sg with weight w:
 //   reference lerp (SonicSim_moving.py:94):  (1 - w) * conv[sg] + w * conv[sg + 1]
 SS_HD void hat_pair(int sg, float w, int p, float& fa, float& fb) {
@@ -341,60 +384,57 @@ SS_HD void hat_pair(int sg, float w, int p, float& fa, float& fb) {
     fb = (sg == p + 1) ? omw : ((sg == p) ? w : 0.f);
 }
 
-// Output row of one CTA.  `first` = this is the first transform of the block (plain store),
-// otherwise the partial result already in `row` is read back and added to (only blocks that
-// straddle a waypoint need a second transform), which keeps 16 accumulators out of the register
-// file during the FFT passes.
-struct MovingSinkBounds {       // compact trajectory (MODE_MOVING_BOUNDS)
-    const int* bounds; float* row; int S, N, nbase, p, sg, b0, b1; double step; bool first;
-    SS_HD MovingSinkBounds(const Source& s, float* row_, int n0, int t, int p_, int sg0, bool first_)
-        : bounds(s.bounds), row(row_), S(s.P - 1), N(s.N), nbase(n0 + t), p(p_), sg(sg0), first(first_) {
-        b0 = bounds[sg]; b1 = bounds[sg + 1]; step = 1.0 / (double)(b1 - b0);
-    }
-    SS_HD void operator()(int r, float2 z) {
-        int n = nbase + 256 * r;
-        if (n >= N) return;
-        if (n >= b1) {
-            do { ++sg; b1 = bounds[sg + 1]; } while (n >= b1);
-            b0 = bounds[sg]; step = 1.0 / (double)(b1 - b0);
-        }
-        float w = (float)((double)(n - b0) * step);      // == np.linspace(0, 1, num, False)[i] as float32
-        float fa, fb;
-        hat_pair(sg, w, p, fa, fb);
-        float v = lerp_terms(fa, z.x, fb, z.y);
-        if (first) row[n] = v; else red_add(row + n, v);
-    }
-};
-struct MovingSinkIndexed {      // per-sample arrays (MODE_MOVING_INDEXED)
-    const int* idx; const float* w; float* row; int N, nbase, p; bool first;
-    SS_HD MovingSinkIndexed(const Source& s, float* row_, int n0, int t, int p_, bool first_)
-        : idx(s.idx), w(s.w), row(row_), N(s.N), nbase(n0 + t), p(p_), first(first_) {}
-    SS_HD void operator()(int r, float2 z) {
-        int n = nbase + 256 * r;
-        if (n >= N) return;
-        float fa, fb;
-        hat_pair(idx[n], w[n], p, fa, fb);
-        float v = lerp_terms(fa, z.x, fb, z.y);
-        if (first) row[n] = v; else red_add(row + n, v);
-    }
-};
-struct StaticSink {             // Re -> channel c0, Im -> channel c1 (row1 null if C is odd)
-    float* row0; float* row1; int N, nbase;
-    SS_HD void operator()(int r, float2 z) {
-        int n = nbase + 256 * r;
-        if (n >= N) return;
-        row0[n] = z.x;
-        if (row1) row1[n] = z.y;
-    }
-};
-
-// min / max interp_index over this thread's 16 samples (indexed mode)
-SS_HD void idx_range(int t, int n0, const Source& s, int& pmin, int& pmax) {
-    pmin = 0x7fffffff; pmax = -1;
+// Output stage of one thread: samples n = n0 + t + 256 r, r = 0..15, visited in order.  `first` = first
+// transform of its block (plain store); the second transform of a block that straddles a waypoint
+// (grid blocking only) accumulates with a fire-and-forget RED - two addends per address, the first
+// stored by this very thread, so the sum is order-free.
+SS_HD void render_epilogue(int t, const XDesc& d, const Regs32& R) {
+    const int nbase = d.n0 + t;
+    if (nbase >= d.n_end) return;
+    if (d.mode == MODE_STATIC) {                             // Re -> channel c, Im -> channel c + 1
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        int n = n0 + t + 256 * r;
-        if (n < s.N) { int sg = s.idx[n]; pmin = sg < pmin ? sg : pmin; pmax = sg > pmax ? sg : pmax; }
+        for (int r = 0; r < 16; ++r) {
+            const int n = nbase + 256 * r;
+            if (n < d.n_end) {
+                const float2 z = R.a[out16(r)];
+                d.row[n] = z.x;
+                if (d.row1) d.row1[n] = z.y;
+            }
+        }
+    } else if (d.mode == MODE_MOVING_BOUNDS) {
+        int sg = d.p_lo;
+        int b1 = d.bounds[sg + 1];
+        while (nbase >= b1) { ++sg; b1 = d.bounds[sg + 1]; }
+        int b0 = d.bounds[sg];
+        double step = d.rstep[sg];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int n = nbase + 256 * r;
+            if (n < d.n_end) {
+                if (n >= b1) {
+                    do { ++sg; b1 = d.bounds[sg + 1]; } while (n >= b1);
+                    b0 = d.bounds[sg]; step = d.rstep[sg];
+                }
+                const float w = (float)((double)(n - b0) * step);   // == np.linspace(0, 1, num, False)[i] as float32
+                float fa, fb;
+                hat_pair(sg, w, d.p, fa, fb);
+                const float2 z = R.a[out16(r)];
+                const float v = lerp_terms(fa, z.x, fb, z.y);
+                if (d.first) d.row[n] = v; else red_add(d.row + n, v);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int n = nbase + 256 * r;
+            if (n < d.n_end) {
+                float fa, fb;
+                hat_pair(d.idx[n], d.w[n], d.p, fa, fb);
+                const float2 z = R.a[out16(r)];
+                const float v = lerp_terms(fa, z.x, fb, z.y);
+                if (d.first) d.row[n] = v; else red_add(d.row + n, v);
+            }
+        }
     }
 }
 

@@ -45,6 +45,7 @@ static void cta_spectra(const Source& S, int local, const Tables& T) {
     const int nh = spectra_pairs_h(S);
     if (local < nh) { ra = make_row_h(S, 2 * local); rb = make_row_h(S, 2 * local + 1); }
     else { local -= nh; ra = make_row_x(S, 2 * local); rb = make_row_x(S, 2 * local + 1); }
+    if (!ra.dst && !rb.dst) return;
     float2* s = smem.data();
     for (int t = 0; t < kThreads; ++t) spectra_phase1(t, ra, rb, s);
     for (int t = 0; t < kThreads; ++t) load2(t, s, R[t]);
@@ -54,28 +55,51 @@ static void cta_spectra(const Source& S, int local, const Tables& T) {
     for (int t = 0; t < kThreads; ++t) spectra_phase4(t, s, ra, rb);
 }
 
-// k_prepare's range CTAs: position range of every block + its work items
-static void prepare_ranges(const Source& S, int si) {
-    for (int b = 0; b < S.nb; ++b) {
-        const int n0 = b * kB;
-        const int n_last = (n0 + kB < S.N ? n0 + kB : S.N) - 1;
-        int p_lo = 0, p_hi = 0;
-        if (S.mode == MODE_MOVING_BOUNDS) {
-            p_lo = seg_of(S.bounds, S.P - 1, n0);
-            p_hi = seg_of(S.bounds, S.P - 1, n_last) + 1;
+// k_blocks: block table, 1 / n_s table, dense item numbering (one source here)
+static void emu_blocks(const Source& S) {
+    int nblk = 0;
+    if (S.aligned) {
+        for (int sg = 0; sg < S.P - 1; ++sg) {
+            const int b0 = S.bounds[sg], n_s = S.bounds[sg + 1] - b0;
+            for (int q = 0; q < seg_blocks(n_s); ++q) {
+                Block bk; bk.start = b0 + kB * q; bk.len = n_s - kB * q < kB ? n_s - kB * q : kB; bk.p_lo = sg; bk.p_hi = sg + 1;
+                S.blocks[nblk++] = bk;
+            }
+        }
+    } else {
+        nblk = S.nb;
+        for (int bi = 0; bi < nblk; ++bi) {
+            Block bk; bk.start = bi * kB; bk.len = S.N - bi * kB < kB ? S.N - bi * kB : kB; bk.p_lo = 0; bk.p_hi = 0;
+            S.blocks[bi] = bk;
+        }
+    }
+    for (int bi = nblk; bi < S.nblk_max; ++bi) { Block z; z.start = 0; z.len = 0; z.p_lo = 0; z.p_hi = 0; S.blocks[bi] = z; }
+    if (S.mode == MODE_MOVING_BOUNDS)
+        for (int sg = 0; sg < S.P - 1; ++sg) S.rstep[sg] = 1.0 / (double)(S.bounds[sg + 1] - S.bounds[sg]);
+    S.counts[0] = nblk;
+    S.counts[1] = 0;
+}
+
+// k_prepare's range CTAs: position range of every block in use + its work items
+static void prepare_ranges(const Source& S, RItem* items) {
+    for (int blk = 0; blk < S.counts[0]; ++blk) {
+        Block bk = S.blocks[blk];
+        if (S.mode == MODE_MOVING_BOUNDS && !S.aligned) {
+            bk.p_lo = seg_of(S.bounds, S.P - 1, bk.start);
+            bk.p_hi = seg_of(S.bounds, S.P - 1, bk.start + bk.len - 1) + 1;
         } else if (S.mode == MODE_MOVING_INDEXED) {
             int pmin = 0x7fffffff, pmax = -1;
-            for (int n = n0; n <= n_last; ++n) { int v = S.idx[n]; pmin = v < pmin ? v : pmin; pmax = v > pmax ? v : pmax; }
-            p_lo = pmin < 0 ? 0 : pmin;
-            p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
+            for (int n = bk.start; n < bk.start + bk.len; ++n) { int v = S.idx[n]; pmin = v < pmin ? v : pmin; pmax = v > pmax ? v : pmax; }
+            bk.p_lo = pmin < 0 ? 0 : pmin;
+            bk.p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
         }
-        for (int lane = 0; lane < 32; ++lane) fill_items(S, si, b, p_lo, p_hi, lane, 32);
+        for (int lane = 0; lane < 32; ++lane) fill_items(S, items, blk, bk, lane, 32);
     }
 }
 
 // One persistent k_render CTA (`cta` of `grid`): same control flow as the kernel; the bulk copies
 // are done at the point where thread 0 issues them, the mbarrier waits are no-ops.
-static void cta_render(const Source* srcs, const RItem* items, int n_items, int cta, int grid, const Tables& T) {
+static void cta_render(const RItem* items, int n_items, int cta, int grid, const Tables& T) {
     std::vector<float2> smem(kPadF + kSpec);
     std::vector<Regs32> R(kThreads);
     float2* const fftbuf = smem.data();
@@ -103,8 +127,7 @@ static void cta_render(const Source* srcs, const RItem* items, int n_items, int 
     for (int k = 0;; ++k) {
         const XDesc& d = s_desc[k & 1];
         if (!d.valid) break;
-        const Source& S = srcs[d.si];
-        for (int t = 0; t < kThreads; ++t) form_z(t, sX, sHp, d.Hq ? sHq : nullptr, d, S.K, R[t]);
+        for (int t = 0; t < kThreads; ++t) form_z(t, sX, sHp, d.Hq ? sHq : nullptr, d, R[t]);
         {   // thread 0: publish transform k+1, stage its Hq
             XDesc nx; memset(&nx, 0, sizeof(nx));
             const RItem& cur = s_item[slot];
@@ -127,22 +150,9 @@ static void cta_render(const Source* srcs, const RItem* items, int n_items, int 
             const XDesc& nx = s_desc[(k + 1) & 1];
             if (nx.valid) { memcpy(sX, nx.X, sizeof(float2) * kSpec); memcpy(sHp, nx.Hp, sizeof(float2) * kSpec); }
         }
-        const int n0 = dcur.b * kB;
         for (int t = 0; t < kThreads; ++t) {
             render_phase3(t, R[t], T);
-            if (S.mode == MODE_MOVING_BOUNDS) {
-                const int nn = n0 + t < S.N ? n0 + t : S.N - 1;
-                int sg0 = dcur.p_lo;
-                while (S.bounds[sg0 + 1] <= nn) ++sg0;
-                MovingSinkBounds sk(S, dcur.row, n0, t, dcur.p, sg0, dcur.first != 0);
-                render_epilogue(R[t], sk);
-            } else if (S.mode == MODE_MOVING_INDEXED) {
-                MovingSinkIndexed sk(S, dcur.row, n0, t, dcur.p, dcur.first != 0);
-                render_epilogue(R[t], sk);
-            } else {
-                StaticSink sk{dcur.row, dcur.Hq ? dcur.row + S.N : nullptr, S.N, n0 + t};
-                render_epilogue(R[t], sk);
-            }
+            render_epilogue(t, dcur, R[t]);
         }
     }
 }
@@ -157,15 +167,21 @@ int emu_render(const float* x, const float* rir, float* out, const int32_t* boun
     memset(&S, 0, sizeof(S));
     S.x = x; S.rir = rir; S.out = out; S.bounds = bounds; S.idx = idx; S.w = w;
     S.N = N; S.P = P; S.C = C; S.L = L; S.K = (L + kB - 1) / kB; S.nb = (N + kB - 1) / kB; S.mode = mode;
-    std::vector<float2> hs((size_t)P * C * S.K * kSpec), xs((size_t)S.nb * kSpec);
-    const int nr = render_ctas(S);
-    std::vector<RItem> items(nr);
-    S.hspec = hs.data(); S.xspec = xs.data(); S.items = items.data();
+    S.aligned = (mode == MODE_MOVING_BOUNDS && S.K == 1) ? 1 : 0;
+    S.nblk_max = S.aligned ? S.nb + P - 1 : S.nb;
+    std::vector<float2> hs((size_t)P * C * S.K * kSpec), xs((size_t)S.nblk_max * kSpec);
+    std::vector<RItem> items(max_render_items(S));
+    std::vector<Block> blocks(S.nblk_max);
+    std::vector<double> rstep(P);
+    int counts[2] = {0, 0};
+    S.hspec = hs.data(); S.xspec = xs.data(); S.blocks = blocks.data(); S.rstep = rstep.data(); S.counts = counts;
+    emu_blocks(S);
     const int ns = spectra_pairs_h(S) + spectra_pairs_x(S);
     for (int i = 0; i < ns; ++i) cta_spectra(S, i, T);
-    prepare_ranges(S, 0);
+    prepare_ranges(S, items.data());
+    const int nr = counts[0] * items_per_block(S);
     const int grid = nr < 3 ? nr : 3;              // a few persistent CTAs, each looping over many items
-    for (int cta = 0; cta < grid; ++cta) cta_render(&S, items.data(), nr, cta, grid, T);
+    for (int cta = 0; cta < grid; ++cta) cta_render(items.data(), nr, cta, grid, T);
     return 0;
 }
 
@@ -175,7 +191,7 @@ int emu_spectra_pair(const float* a, const float* b, int len, float* specA, floa
     Source S; memset(&S, 0, sizeof(S));
     std::vector<float> rir(2 * (size_t)len);
     memcpy(rir.data(), a, sizeof(float) * len); memcpy(rir.data() + len, b, sizeof(float) * len);
-    S.rir = rir.data(); S.P = 1; S.C = 2; S.L = len; S.K = (len + kB - 1) / kB; S.N = 1; S.nb = 1;
+    S.rir = rir.data(); S.P = 1; S.C = 2; S.L = len; S.K = (len + kB - 1) / kB; S.N = 1; S.nb = 1; S.nblk_max = 0;
     std::vector<float2> hs((size_t)2 * S.K * kSpec);
     S.hspec = hs.data();
     for (int i = 0; i < spectra_pairs_h(S); ++i) cta_spectra(S, i, T);

@@ -38,7 +38,9 @@ def test_golden_moving_both_trajectory_forms(emu, golden):
         y_idx = emu.render(x, h, idx=idx, w=w, mode=2)
         y_bnd = emu.render(x, h, bounds=bounds_of(idx, h.shape[0]), mode=1)
         assert so.rel_rms(y_idx, g[f"y{k}"]) < TOL
-        assert np.array_equal(y_idx, y_bnd)        # device-side linspace weights are bit-identical to numpy's
+        # same weights bit for bit (device-side linspace == numpy's); the two forms block the signal
+        # differently (waypoint-aligned vs fixed grid), so they agree to fp32 rounding, not bitwise
+        assert so.rel_rms(y_bnd, g[f"y{k}"]) < TOL and so.rel_rms(y_idx, y_bnd) < 2e-6
 
 
 @pytest.mark.parametrize("P,C,L,N", [(3, 1, 1, 100), (2, 2, 4096, 4096), (2, 1, 4097, 8193), (9, 3, 600, 12289),

@@ -38,7 +38,7 @@ def test_cfg3_scene_batch_60s_60pt():
     assert so.rel_rms(ym[0], so.convolve_moving_receiver(moving[0][0], moving[0][1], idx, w)) < TOL
     assert so.rel_rms(ys[1], so.convolve_fixed_receiver(static[1][0][None], static[1][1])) < TOL
     idx2, w2 = so.setup_dynamic_interp(moving[1][2], N)
-    assert np.array_equal(ym[1], sm.convolve_moving_receiver(moving[1][0], moving[1][1], idx2, w2))
+    assert so.rel_rms(ym[1], sm.convolve_moving_receiver(moving[1][0], moving[1][1], idx2, w2)) < 2e-6   # aligned vs grid blocking
     assert np.array_equal(ys[0], sm.convolve_fixed_receiver(static[0][0][None], static[0][1]))
 
 
