@@ -169,7 +169,7 @@ def run_ours(args, rank, local_rank, world):
     C, N = CFG["C"], CFG["N"]
 
     # ---- device-resident arm
-    d_srcs = [render.MovingSource(torch.from_numpy(x).to(dev), torch.from_numpy(h).to(dev), torch.from_numpy(b).to(dev))
+    d_srcs = [render.MovingSource(torch.from_numpy(x).to(dev), torch.from_numpy(h).to(dev), torch.from_numpy(b).to(dev), b)
               for x, h, b in items]
     d_outs = [torch.empty((C, N), dtype=torch.float32, device=dev) for _ in range(n_src)]
     step_alg = sum(alg_bytes_moving(N, CFG["P"], C, CFG["L"]) for _ in items)

@@ -56,6 +56,8 @@ typedef struct {
     int32_t N, P, C, L;
     int32_t mode;             /* ss_mode */
     int32_t reserved;
+    const int32_t* bounds_host; /* ss_render_dev only, optional: HOST copy of `bounds` (P ints).  With it the block
+                                 * table is built on the host and one small kernel launch per chunk is saved.     */
 } ss_source;
 
 /* library / build identification */

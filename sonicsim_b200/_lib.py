@@ -50,7 +50,7 @@ class SsSource(ctypes.Structure):
     _fields_ = [("x", ctypes.c_void_p), ("rir", ctypes.c_void_p), ("out", ctypes.c_void_p),
                 ("bounds", ctypes.c_void_p), ("idx", ctypes.c_void_p), ("w", ctypes.c_void_p),
                 ("N", ctypes.c_int32), ("P", ctypes.c_int32), ("C", ctypes.c_int32), ("L", ctypes.c_int32),
-                ("mode", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("mode", ctypes.c_int32), ("reserved", ctypes.c_int32), ("bounds_host", ctypes.c_void_p)]
 
 
 def _stale():

@@ -9,7 +9,7 @@
 struct ss_ctx {
     int device = 0;
     int sm_count = 148;
-    int64_t chunk_bytes = 48ll << 20;
+    int64_t chunk_bytes = 96ll << 20;
     // scratch for spectra
     char* d_scratch = nullptr; size_t scratch_cap = 0;
     // descriptor ring (pinned host + device)

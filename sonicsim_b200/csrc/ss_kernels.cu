@@ -424,6 +424,31 @@ static size_t spectra_bytes(const ss_source& it) {
            align_up(sizeof(Block) * (size_t)sh.nblk_max, 256) + align_up(sizeof(double) * (size_t)it.P, 256) + 256;
 }
 
+// Host-side twin of k_blocks for one source whose trajectory bounds are visible on the host.
+// Returns the number of blocks in use.
+static int build_blocks_host(const ss_source& it, const Shape& sh, const int32_t* hb, Block* blocks, double* rstep) {
+    int nblk = 0;
+    if (sh.aligned) {
+        for (int sg = 0; sg < it.P - 1; ++sg) {
+            const int b0 = hb[sg], n_s = hb[sg + 1] - b0;
+            for (int q = 0; q < seg_blocks(n_s); ++q) {
+                Block bk; bk.start = b0 + kB * q; bk.len = n_s - kB * q < kB ? n_s - kB * q : kB; bk.p_lo = sg; bk.p_hi = sg + 1;
+                blocks[nblk++] = bk;
+            }
+        }
+    } else {
+        nblk = sh.nb;
+        for (int bi = 0; bi < nblk; ++bi) {
+            Block bk; bk.start = bi * kB; bk.len = it.N - bi * kB < kB ? it.N - bi * kB : kB; bk.p_lo = 0; bk.p_hi = 0;
+            blocks[bi] = bk;
+        }
+    }
+    for (int bi = nblk; bi < sh.nblk_max; ++bi) { Block z; z.start = 0; z.len = 0; z.p_lo = 0; z.p_hi = 0; blocks[bi] = z; }
+    if (it.mode == SS_MOVING_BOUNDS && hb)
+        for (int sg = 0; sg < it.P - 1; ++sg) rstep[sg] = 1.0 / (double)(hb[sg + 1] - hb[sg]);
+    return nblk;
+}
+
 // Enqueue the three launches for items[first, last) (device pointers) on `stream`.
 static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, cudaStream_t stream) {
     const int n = last - first;
@@ -437,9 +462,19 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
         CK(cudaMalloc(&c->d_scratch, cap));
         c->scratch_cap = cap;
     }
-    // descriptor block: Source[n] | prefix_prepare[n+1]
+    // Block tables on the host when every trajectory is host-visible (always true on the host path)
+    bool host_tables = true;
+    for (int i = first; i < last; ++i)
+        if (items[i].mode == SS_MOVING_BOUNDS && !items[i].bounds_host) host_tables = false;
+    // descriptor block: Source[n] | prefix_prepare[n+1] | total | per source: blocks, rstep, counts
     const size_t off_ps = align_up(sizeof(Source) * n, 16);
-    const size_t bytes = off_ps + align_up(sizeof(int) * (n + 1), 16);
+    const size_t off_tot = off_ps + align_up(sizeof(int) * (n + 1), 16);
+    size_t bytes = off_tot + 16;
+    if (host_tables)
+        for (int i = first; i < last; ++i) {
+            const Shape sh = shape_of(items[i]);
+            bytes += align_up(sizeof(Block) * (size_t)sh.nblk_max, 16) + align_up(sizeof(double) * (size_t)items[i].P, 16) + 16;
+        }
     const int slot = c->ring_pos; c->ring_pos = (c->ring_pos + 1) % ss_ctx::kRing;
     if (bytes > c->desc_cap[slot]) {
         CK(cudaEventSynchronize(c->desc_ev[slot]));
@@ -456,7 +491,8 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
     Source* hs = (Source*)c->h_desc[slot];
     int* hps = (int*)(c->h_desc[slot] + off_ps);
     char* scratch = c->d_scratch;
-    int ps = 0, pr = 0;
+    int ps = 0, pr = 0, total_items = 0;
+    size_t tab_off = off_tot + 16;
     for (int i = 0; i < n; ++i) {
         const ss_source& it = items[first + i];
         const Shape sh = shape_of(it);
@@ -470,18 +506,33 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
         s.K = sh.K; s.nb = sh.nb; s.mode = it.mode; s.aligned = sh.aligned; s.nblk_max = sh.nblk_max;
         s.hspec = (float2*)scratch; scratch += (size_t)s.P * s.C * s.K * kSpec * sizeof(float2);
         s.xspec = (float2*)scratch; scratch += (size_t)s.nblk_max * kSpec * sizeof(float2);
-        s.blocks = (Block*)scratch; scratch += align_up(sizeof(Block) * (size_t)s.nblk_max, 256);
-        s.rstep = (double*)scratch; scratch += align_up(sizeof(double) * (size_t)s.P, 256);
-        s.counts = (int*)scratch; scratch += 256;
+        if (host_tables) {
+            // tables live in the descriptor block itself: filled here, copied with it
+            char* hbase = c->h_desc[slot]; char* dbase = c->d_desc[slot];
+            Block* hb_blocks = (Block*)(hbase + tab_off);
+            s.blocks = (Block*)(dbase + tab_off); tab_off += align_up(sizeof(Block) * (size_t)s.nblk_max, 16);
+            double* hb_rstep = (double*)(hbase + tab_off);
+            s.rstep = (double*)(dbase + tab_off); tab_off += align_up(sizeof(double) * (size_t)s.P, 16);
+            int* hb_counts = (int*)(hbase + tab_off);
+            s.counts = (int*)(dbase + tab_off); tab_off += 16;
+            const int nblk = build_blocks_host(it, sh, it.bounds_host, hb_blocks, hb_rstep);
+            hb_counts[0] = nblk; hb_counts[1] = total_items; hb_counts[2] = 0; hb_counts[3] = 0;
+            total_items += nblk * sh.per;
+        } else {
+            s.blocks = (Block*)scratch; scratch += align_up(sizeof(Block) * (size_t)s.nblk_max, 256);
+            s.rstep = (double*)scratch; scratch += align_up(sizeof(double) * (size_t)s.P, 256);
+            s.counts = (int*)scratch; scratch += 256;
+        }
         hs[i] = s;
         hps[i] = ps;
         ps += spectra_pairs_h(s) + spectra_pairs_x(s) + range_ctas(s);
         pr += sh.max_items;
     }
     hps[n] = ps;
-    // work-item table of the whole chunk (dense, filled through the k_blocks scan) + its length
+    // work-item table of the whole chunk (dense) + its length
     RItem* d_items = (RItem*)scratch; scratch += (size_t)pr * sizeof(RItem);
-    int* d_total = (int*)scratch;
+    int* d_total = host_tables ? (int*)(c->d_desc[slot] + off_tot) : (int*)scratch;
+    if (host_tables) { *(int*)(c->h_desc[slot] + off_tot) = total_items; pr = total_items; }
     CK(cudaMemcpyAsync(c->d_desc[slot], c->h_desc[slot], bytes, cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(c->desc_ev[slot], stream));
     const Source* ds = (const Source*)c->d_desc[slot];
@@ -491,8 +542,11 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
         CK(cudaEventCreate(&pf.e0)); CK(cudaEventCreate(&pf.e1)); CK(cudaEventCreate(&pf.e2));
         CK(cudaEventRecord(pf.e0, stream));
     }
-    k_blocks<<<1, 256, 0, stream>>>(ds, n, d_total);
-    CK(cudaGetLastError());
+    if (!host_tables) {
+        k_blocks<<<1, 256, 0, stream>>>(ds, n, d_total);
+        CK(cudaGetLastError());
+        c->launches += 1;
+    }
     k_prepare<<<ps, kThreads, kPadF * (int)sizeof(float2), stream>>>(ds, dps, n, d_items);
     CK(cudaGetLastError());
     if (c->profiling) CK(cudaEventRecord(pf.e1, stream));
@@ -500,7 +554,7 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
     k_render<<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total);
     CK(cudaGetLastError());
     if (c->profiling) { CK(cudaEventRecord(pf.e2, stream)); c->prof.push_back(pf); }
-    c->launches += 3;
+    c->launches += 2;
     return SS_OK;
 }
 
@@ -520,7 +574,14 @@ extern "C" int ss_render_dev(ss_ctx* c, const ss_source* items, int n_items, voi
     if (!c || (!items && n_items > 0) || n_items < 0) return SS_ERR_INVALID;
     if (n_items == 0) return SS_OK;
     CK(cudaSetDevice(c->device));
-    for (int i = 0; i < n_items; ++i) { int st = validate_item(items[i]); if (st) return st; }
+    for (int i = 0; i < n_items; ++i) {
+        int st = validate_item(items[i]); if (st) return st;
+        if (items[i].mode == SS_MOVING_BOUNDS && items[i].bounds_host) {
+            const int32_t* b = items[i].bounds_host;
+            if (b[0] != 0 || b[items[i].P - 1] != items[i].N) return SS_ERR_INVALID;
+            for (int q = 0; q + 1 < items[i].P; ++q) if (b[q + 1] < b[q]) return SS_ERR_INVALID;
+        }
+    }
     std::vector<int> cuts;
     make_chunks(c, items, n_items, cuts);
     for (size_t k = 0; k + 1 < cuts.size(); ++k) {
@@ -606,6 +667,7 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
             if (it.mode == SS_MOVING_BOUNDS) {
                 nb = sizeof(int32_t) * (size_t)it.P;
                 CK(cudaMemcpyAsync(pi, it.bounds, nb, cudaMemcpyHostToDevice, c->s_in)); d.bounds = (const int32_t*)pi; pi += align_up(nb, 256);
+                d.bounds_host = it.bounds;
             } else if (it.mode == SS_MOVING_INDEXED) {
                 nb = 4 * (size_t)it.N;
                 CK(cudaMemcpyAsync(pi, it.idx, nb, cudaMemcpyHostToDevice, c->s_in)); d.idx = (const int32_t*)pi; pi += align_up(nb, 256);

@@ -158,52 +158,50 @@ SS_HD int find_source(const int* prefix, int n, int v) {
 // A "row" is 8192 samples  a[n] = (0 <= g0 + n < len && n < ncap) ? base[g0 + n] : 0.
 // =======================================================================================
 struct Row {
-    const float* base;
-    float2* dst;           // null -> row absent (odd count)
-    int g0, len, ncap;
+    const float* src;      // base + g0: sample n of the row is src[n] for n in [nlo, nhi), zero elsewhere
+    float2* dst;           // null -> row absent (odd count / unused block slot)
+    int nlo, nspan;        // nspan = nhi - nlo (0: empty)
     float scale;
 };
+SS_HD Row make_row(const float* base, float2* dst, int g0, int len, int ncap, float scale) {
+    Row r;
+    r.dst = dst; r.scale = scale;
+    int nlo = g0 < 0 ? -g0 : 0;
+    int nhi = len - g0 < ncap ? len - g0 : ncap;
+    r.nlo = nlo; r.nspan = nhi > nlo ? nhi - nlo : 0;
+    r.src = base + g0;
+    return r;
+}
+SS_HD Row no_row() { Row r; r.src = nullptr; r.dst = nullptr; r.nlo = 0; r.nspan = 0; r.scale = 0.f; return r; }
 
 SS_HD Row make_row_h(const Source& s, int row) {
-    Row r;
-    if (row >= s.P * s.C * s.K) { r.base = nullptr; r.dst = nullptr; r.g0 = 0; r.len = 0; r.ncap = 0; r.scale = 0.f; return r; }
+    if (row >= s.P * s.C * s.K) return no_row();
     int part = row % s.K, pc = row / s.K;
-    r.base = s.rir + (size_t)pc * s.L;
-    r.dst = s.hspec + (size_t)row * kSpec;
-    r.g0 = part * kB; r.len = s.L; r.ncap = kB;
-    r.scale = 1.0f / (float)kF;
-    return r;
+    return make_row(s.rir + (size_t)pc * s.L, s.hspec + (size_t)row * kSpec, part * kB, s.L, kB, 1.0f / (float)kF);
 }
 SS_HD Row make_row_x(const Source& s, int blk) {
-    Row r;
-    r.base = nullptr; r.dst = nullptr; r.g0 = 0; r.len = 0; r.ncap = 0; r.scale = 0.f;
-    if (blk >= s.nblk_max) return r;
+    if (blk >= s.nblk_max) return no_row();
     const Block bk = s.blocks[blk];
-    if (bk.len == 0) return r;
-    r.base = s.x;
-    r.dst = s.xspec + (size_t)blk * kSpec;
-    r.g0 = bk.start - kB; r.len = s.N; r.ncap = kF;
-    r.scale = 1.0f;
-    return r;
+    if (bk.len == 0) return no_row();
+    return make_row(s.x, s.xspec + (size_t)blk * kSpec, bk.start - kB, s.N, kF, 1.0f);
 }
 SS_HD float row_at(const Row& r, int n) {
-    int g = r.g0 + n;
-    return (r.dst != nullptr && n < r.ncap && g >= 0 && g < r.len) ? r.base[g] : 0.f;
+    return ((unsigned)(n - r.nlo) < (unsigned)r.nspan) ? r.src[n] : 0.f;
 }
 
 struct Regs32 { float2 a[16]; float2 b[16]; };
 
-// S1: pass A of the forward transform straight from global memory.
+// S1: pass A of the forward transform straight from global memory: all 64 loads of the thread's two
+// butterflies are issued before the first butterfly is computed (one exposed memory latency, not two).
 SS_HD void spectra_phase1(int t, const Row& ra, const Row& rb, float2* s) {
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-        int j = t + 256 * h;
-        float2 v[16];
+    Regs32 R;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = make_float2(row_at(ra, j + 512 * r), row_at(rb, j + 512 * r));
-        fft16<false>(v);
-        passA_store(s, j, v);
+    for (int r = 0; r < 16; ++r) {
+        R.a[r] = make_float2(row_at(ra, t + 512 * r), row_at(rb, t + 512 * r));
+        R.b[r] = make_float2(row_at(ra, t + 256 + 512 * r), row_at(rb, t + 256 + 512 * r));
     }
+    fft16<false>(R.a); passA_store(s, t, R.a);
+    fft16<false>(R.b); passA_store(s, t + 256, R.b);
 }
 // generic "load both butterflies t and t+256":  pad(t + 256) = pad(t) + 272
 SS_HD void load2(int t, const float2* s, Regs32& R) {
@@ -389,50 +387,59 @@ SS_HD void hat_pair(int sg, float w, int p, float& fa, float& fb) {
 // (grid blocking only) accumulates with a fire-and-forget RED - two addends per address, the first
 // stored by this very thread, so the sum is order-free.
 SS_HD void render_epilogue(int t, const XDesc& d, const Regs32& R) {
-    const int nbase = d.n0 + t;
-    if (nbase >= d.n_end) return;
-    if (d.mode == MODE_STATIC) {                             // Re -> channel c, Im -> channel c + 1
+    // `d` lives in shared memory: copy what the loop needs into registers once - after every global
+    // store the compiler would otherwise have to reload each field (generic pointers may alias)
+    const int nbase = d.n0 + t, n_end = d.n_end, mode = d.mode, p = d.p;
+    float* const row = d.row;
+    const bool first = d.first != 0;
+    if (nbase >= n_end) return;
+    if (mode == MODE_STATIC) {                               // Re -> channel c, Im -> channel c + 1
+        float* const row1 = d.row1;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const int n = nbase + 256 * r;
-            if (n < d.n_end) {
+            if (n < n_end) {
                 const float2 z = R.a[out16(r)];
-                d.row[n] = z.x;
-                if (d.row1) d.row1[n] = z.y;
+                row[n] = z.x;
+                if (row1) row1[n] = z.y;
             }
         }
-    } else if (d.mode == MODE_MOVING_BOUNDS) {
+    } else if (mode == MODE_MOVING_BOUNDS) {
+        const int* const bounds = d.bounds;
+        const double* const rstep = d.rstep;
         int sg = d.p_lo;
-        int b1 = d.bounds[sg + 1];
-        while (nbase >= b1) { ++sg; b1 = d.bounds[sg + 1]; }
-        int b0 = d.bounds[sg];
-        double step = d.rstep[sg];
+        int b1 = bounds[sg + 1];
+        while (nbase >= b1) { ++sg; b1 = bounds[sg + 1]; }
+        int b0 = bounds[sg];
+        double step = rstep[sg];
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const int n = nbase + 256 * r;
-            if (n < d.n_end) {
+            if (n < n_end) {
                 if (n >= b1) {
-                    do { ++sg; b1 = d.bounds[sg + 1]; } while (n >= b1);
-                    b0 = d.bounds[sg]; step = d.rstep[sg];
+                    do { ++sg; b1 = bounds[sg + 1]; } while (n >= b1);
+                    b0 = bounds[sg]; step = rstep[sg];
                 }
                 const float w = (float)((double)(n - b0) * step);   // == np.linspace(0, 1, num, False)[i] as float32
                 float fa, fb;
-                hat_pair(sg, w, d.p, fa, fb);
+                hat_pair(sg, w, p, fa, fb);
                 const float2 z = R.a[out16(r)];
                 const float v = lerp_terms(fa, z.x, fb, z.y);
-                if (d.first) d.row[n] = v; else red_add(d.row + n, v);
+                if (first) row[n] = v; else red_add(row + n, v);
             }
         }
     } else {
+        const int* const idx = d.idx;
+        const float* const wv = d.w;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const int n = nbase + 256 * r;
-            if (n < d.n_end) {
+            if (n < n_end) {
                 float fa, fb;
-                hat_pair(d.idx[n], d.w[n], d.p, fa, fb);
+                hat_pair(idx[n], wv[n], p, fa, fb);
                 const float2 z = R.a[out16(r)];
                 const float v = lerp_terms(fa, z.x, fb, z.y);
-                if (d.first) d.row[n] = v; else red_add(d.row + n, v);
+                if (first) row[n] = v; else red_add(row + n, v);
             }
         }
     }

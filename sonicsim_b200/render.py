@@ -16,10 +16,13 @@ from .SonicSim_moving import _as_f32, _samples_per_interval, bounds_from_counts
 
 
 class MovingSource(T.NamedTuple):
-    """One moving source: dry (N,), RIRs (P, C, L), trajectory as int32 segment bounds (P,)."""
+    """One moving source: dry (N,), RIRs (P, C, L), trajectory as int32 segment bounds (P,).
+    `bounds_host` (device path only, optional): NumPy copy of `bounds`; lets the library build the block
+    table on the host instead of launching one more small kernel."""
     dry: T.Any
     rirs: T.Any
     bounds: T.Any
+    bounds_host: T.Any = None
 
 
 class StaticSource(T.NamedTuple):
@@ -98,6 +101,7 @@ class Renderer:
         import torch
         n = len(sources)
         items = (SsSource * n)()
+        keep = []
         for i, s in enumerate(sources):
             if isinstance(s, StaticSource):
                 C, L = s.rir.shape
@@ -105,9 +109,13 @@ class Renderer:
                                     N=s.dry.numel(), P=1, C=C, L=L, mode=_lib.SS_STATIC)
             else:
                 P, C, L = s.rirs.shape
+                bh = None
+                if s.bounds_host is not None:
+                    bh = np.ascontiguousarray(s.bounds_host, dtype=np.int32)
+                    keep.append(bh)
                 items[i] = SsSource(x=s.dry.data_ptr(), rir=s.rirs.data_ptr(), out=outs[i].data_ptr(),
                                     bounds=s.bounds.data_ptr(), N=s.dry.numel(), P=P, C=C, L=L,
-                                    mode=_lib.SS_MOVING_BOUNDS)
+                                    mode=_lib.SS_MOVING_BOUNDS, bounds_host=bh.ctypes.data if bh is not None else None)
         if stream is None:
             stream = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.ss_render_dev(self.ctx, items, n, ctypes.c_void_p(stream)))
