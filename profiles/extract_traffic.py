@@ -26,9 +26,9 @@ def metrics(path):
 
 if __name__ == "__main__":
     r, p, tag = sys.argv[1], sys.argv[2], sys.argv[3]
-    out = {"tag": tag, "sources_per_launch": 4,
-           "note": "ncu --set full --clock-control none, bench.py --utterances 4 (8 cfg2 sources per step, 48 MB chunk budget -> "
-                   "4 sources per launch, the same launch size as the default bench)",
+    out = {"tag": tag, "sources_per_launch": 7,
+           "note": "ncu --set full --clock-control none, bench.py --utterances 7 (14 cfg2 sources per step, 96 MB chunk budget -> "
+                   "7 sources per launch, the same launch size as the default bench)",
            "k_render": metrics(r), "k_prepare": metrics(p)}
     json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))

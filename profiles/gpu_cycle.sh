@@ -13,7 +13,7 @@ print("BENCH $TAG value %.0f ms/step %.3f | k_render %.1f us k_prepare %.1f us f
   d["value"], d["ms_per_step"], 1e3*r["kernel_ms"], 1e3*r["k_prepare_ms"], r["frac"], r["path_frac"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["clocks"]))
 PY
 tail -3 gpurun_out/bench_$TAG.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --utterances 4 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_render -s 2 -c 1 -o gpurun_out/prof_render_$TAG python bench.py --steps 1 --warmup 3 --utterances 4 --no-cpu-baseline > gpurun_out/ncu_render.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_prepare -s 2 -c 1 -o gpurun_out/prof_prepare_$TAG python bench.py --steps 1 --warmup 3 --utterances 4 --no-cpu-baseline > gpurun_out/ncu_spectra.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --utterances 7 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_render -s 2 -c 1 -o gpurun_out/prof_render_$TAG python bench.py --steps 1 --warmup 3 --utterances 7 --no-cpu-baseline > gpurun_out/ncu_render.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_prepare -s 2 -c 1 -o gpurun_out/prof_prepare_$TAG python bench.py --steps 1 --warmup 3 --utterances 7 --no-cpu-baseline > gpurun_out/ncu_spectra.log 2>&1
 ls gpurun_out | tr '\n' ' '

@@ -11,7 +11,11 @@ struct ss_ctx {
     int sm_count = 148;
     int64_t chunk_bytes = 96ll << 20;
     // scratch for spectra
-    char* d_scratch = nullptr; size_t scratch_cap = 0;
+    // two scratch buffers: consecutive chunks of ss_render_dev alternate between them (and between two
+    // internal streams) so that chunk i+1's descriptor copy + k_prepare overlap chunk i's k_render tail
+    char* d_scratch[2] = {nullptr, nullptr}; size_t scratch_cap[2] = {0, 0};
+    cudaStream_t s_aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     // descriptor ring (pinned host + device)
     static const int kRing = 4;
     char* h_desc[kRing] = {nullptr, nullptr, nullptr, nullptr};
@@ -24,6 +28,7 @@ struct ss_ctx {
     struct Slot { char* d_in = nullptr; size_t in_cap = 0; char* d_out = nullptr; size_t out_cap = 0;
                   cudaEvent_t ev_in, ev_done, ev_free; } slot[2];
     int64_t launches = 0;
+    bool single_stream = false;   // experiment knob (SS_SINGLE_STREAM=1): no chunk overlap
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Prof { cudaEvent_t e0, e1, e2; };

@@ -326,6 +326,11 @@ extern "C" int ss_create(int device, ss_ctx** out) {
     CK(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
     CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
     for (int i = 0; i < ss_ctx::kRing; ++i) CK(cudaEventCreateWithFlags(&c->desc_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
@@ -334,6 +339,7 @@ extern "C" int ss_create(int device, ss_ctx** out) {
         CK(cudaEventCreateWithFlags(&c->slot[i].ev_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->slot[i].ev_free, cudaEventDisableTiming));
     }
+    c->single_stream = getenv("SS_SINGLE_STREAM") != nullptr;
     *out = c;
     return SS_OK;
 }
@@ -342,7 +348,12 @@ extern "C" void ss_destroy(ss_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    if (c->d_scratch) cudaFree(c->d_scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (c->d_scratch[i]) cudaFree(c->d_scratch[i]);
+        if (c->s_aux[i]) cudaStreamDestroy(c->s_aux[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int i = 0; i < ss_ctx::kRing; ++i) {
         if (c->h_desc[i]) cudaFreeHost(c->h_desc[i]);
         if (c->d_desc[i]) cudaFree(c->d_desc[i]);
@@ -450,17 +461,17 @@ static int build_blocks_host(const ss_source& it, const Shape& sh, const int32_t
 }
 
 // Enqueue the three launches for items[first, last) (device pointers) on `stream`.
-static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, cudaStream_t stream) {
+static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, cudaStream_t stream, int buf = 0) {
     const int n = last - first;
     size_t need = 256;
     for (int i = first; i < last; ++i) need += spectra_bytes(items[i]);
-    if (need > c->scratch_cap) {
+    if (need > c->scratch_cap[buf]) {
         CK(cudaDeviceSynchronize());
-        if (c->d_scratch) CK(cudaFree(c->d_scratch));
-        c->d_scratch = nullptr; c->scratch_cap = 0;
+        if (c->d_scratch[buf]) CK(cudaFree(c->d_scratch[buf]));
+        c->d_scratch[buf] = nullptr; c->scratch_cap[buf] = 0;
         size_t cap = align_up(need + need / 4, 1 << 20);
-        CK(cudaMalloc(&c->d_scratch, cap));
-        c->scratch_cap = cap;
+        CK(cudaMalloc(&c->d_scratch[buf], cap));
+        c->scratch_cap[buf] = cap;
     }
     // Block tables on the host when every trajectory is host-visible (always true on the host path)
     bool host_tables = true;
@@ -490,7 +501,7 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
     }
     Source* hs = (Source*)c->h_desc[slot];
     int* hps = (int*)(c->h_desc[slot] + off_ps);
-    char* scratch = c->d_scratch;
+    char* scratch = c->d_scratch[buf];
     int ps = 0, pr = 0, total_items = 0;
     size_t tab_off = off_tot + 16;
     for (int i = 0; i < n; ++i) {
@@ -584,11 +595,26 @@ extern "C" int ss_render_dev(ss_ctx* c, const ss_source* items, int n_items, voi
     }
     std::vector<int> cuts;
     make_chunks(c, items, n_items, cuts);
-    for (size_t k = 0; k + 1 < cuts.size(); ++k) {
-        int st = launch_chunk(c, items, cuts[k], cuts[k + 1], (cudaStream_t)stream);
-        if (st) return st;
+    const size_t n_chunks = cuts.size() - 1;
+    if (n_chunks < 2 || c->single_stream || c->profiling) {      // profiling: kernels serialised -> clean per-kernel times
+        for (size_t k = 0; k < n_chunks; ++k) {
+            int st = launch_chunk(c, items, cuts[k], cuts[k + 1], (cudaStream_t)stream, 0);
+            if (st) return st;
+        }
+        return SS_OK;
     }
-    return SS_OK;
+    // fork: chunks alternate between two internal streams / scratch buffers; join back into `stream`
+    CK(cudaEventRecord(c->ev_fork, (cudaStream_t)stream));
+    CK(cudaStreamWaitEvent(c->s_aux[0], c->ev_fork, 0));
+    CK(cudaStreamWaitEvent(c->s_aux[1], c->ev_fork, 0));
+    int rc = SS_OK;
+    for (size_t k = 0; k < n_chunks && rc == SS_OK; ++k)
+        rc = launch_chunk(c, items, cuts[k], cuts[k + 1], c->s_aux[k & 1], (int)(k & 1));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventRecord(c->ev_join[i], c->s_aux[i]));
+        CK(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_join[i], 0));
+    }
+    return rc;
 }
 
 // ----------------------------------------------------------------------------- host path

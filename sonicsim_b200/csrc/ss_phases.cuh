@@ -75,13 +75,14 @@ struct XDesc {
     const double* rstep;
     const int* idx;
     const float* w;
-    int n0, n_end, p, p_lo;
+    int n0, n_end, p, p_lo, p_hi;
     int first;             // first transform of its block: plain store, otherwise accumulate
     int valid;
     int mode;
     int kparts;
+    int pad_;
 };
-static_assert(sizeof(XDesc) == 104, "XDesc layout");
+static_assert(sizeof(XDesc) == 112, "XDesc layout");
 
 SS_HD int spectra_pairs_h(const Source& s) { return (s.P * s.C * s.K + 1) >> 1; }
 SS_HD int spectra_pairs_x(const Source& s) { return (s.nblk_max + 1) >> 1; }
@@ -135,7 +136,7 @@ SS_HD XDesc make_xdesc(const RItem& it, int p) {
     d.Hq = has_q ? d.Hp + it.pstride : nullptr;
     d.row = it.row; d.row1 = it.row1;
     d.bounds = it.bounds; d.rstep = it.rstep; d.idx = it.idx; d.w = it.w;
-    d.n0 = it.n0; d.n_end = it.n_end; d.p = p; d.p_lo = it.p_lo;
+    d.n0 = it.n0; d.n_end = it.n_end; d.p = p; d.p_lo = it.p_lo; d.p_hi = it.p_hi; d.pad_ = 0;
     d.first = (p == it.p_lo);
     d.valid = 1;
     d.mode = it.mode;
@@ -404,6 +405,20 @@ SS_HD void render_epilogue(int t, const XDesc& d, const Regs32& R) {
                 if (row1) row1[n] = z.y;
             }
         }
+    } else if (mode == MODE_MOVING_BOUNDS && d.p_lo + 1 == d.p_hi) {
+        // the block lies inside one segment (always so under aligned blocking): sg = p for every
+        // sample, 16 independent weight computations, lerp = (1 - w) Re z + w Im z
+        const int b0 = d.bounds[p];
+        const double step = d.rstep[p];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int n = nbase + 256 * r;
+            if (n < n_end) {
+                const float w = (float)((double)(n - b0) * step);   // == np.linspace(0, 1, num, False)[i] as float32
+                const float2 z = R.a[out16(r)];
+                row[n] = lerp_terms(one_minus(w), z.x, w, z.y);
+            }
+        }
     } else if (mode == MODE_MOVING_BOUNDS) {
         const int* const bounds = d.bounds;
         const double* const rstep = d.rstep;
@@ -420,7 +435,7 @@ SS_HD void render_epilogue(int t, const XDesc& d, const Regs32& R) {
                     do { ++sg; b1 = bounds[sg + 1]; } while (n >= b1);
                     b0 = bounds[sg]; step = rstep[sg];
                 }
-                const float w = (float)((double)(n - b0) * step);   // == np.linspace(0, 1, num, False)[i] as float32
+                const float w = (float)((double)(n - b0) * step);
                 float fa, fb;
                 hat_pair(sg, w, p, fa, fb);
                 const float2 z = R.a[out16(r)];
