@@ -9,7 +9,8 @@
 struct ss_ctx {
     int device = 0;
     int sm_count = 148;
-    int64_t chunk_bytes = 96ll << 20;
+    int64_t chunk_bytes = 96ll << 20;        // device path: launch granularity (bigger = better amortised)
+    int64_t chunk_bytes_host = 28ll << 20;   // host path: copy/compute/copy pipeline granularity (PCIe-bound)
     // scratch for spectra
     // two scratch buffers: consecutive chunks of ss_render_dev alternate between them (and between two
     // internal streams) so that chunk i+1's descriptor copy + k_prepare overlap chunk i's k_render tail
@@ -26,7 +27,8 @@ struct ss_ctx {
     // host path
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
     struct Slot { char* d_in = nullptr; size_t in_cap = 0; char* d_out = nullptr; size_t out_cap = 0;
-                  cudaEvent_t ev_in, ev_done, ev_free; } slot[2];
+                  cudaEvent_t ev_in, ev_done, ev_free; } slot[4];
+    static const int kSlots = 4;   // H2D may run up to 3 chunks ahead of the D2H that frees a slot
     int64_t launches = 0;
     bool single_stream = false;   // experiment knob (SS_SINGLE_STREAM=1): no chunk overlap
     // optional per-kernel timing (CUDA events on the launching stream)

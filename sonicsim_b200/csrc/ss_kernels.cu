@@ -334,12 +334,13 @@ extern "C" int ss_create(int device, ss_ctx** out) {
     CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ss_ctx::kSlots; ++i) {
         CK(cudaEventCreateWithFlags(&c->slot[i].ev_in, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->slot[i].ev_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->slot[i].ev_free, cudaEventDisableTiming));
     }
     c->single_stream = getenv("SS_SINGLE_STREAM") != nullptr;
+    if (getenv("SS_HOST_CHUNK_MB")) c->chunk_bytes_host = (int64_t)atoi(getenv("SS_HOST_CHUNK_MB")) << 20;
     *out = c;
     return SS_OK;
 }
@@ -359,7 +360,7 @@ extern "C" void ss_destroy(ss_ctx* c) {
         if (c->d_desc[i]) cudaFree(c->d_desc[i]);
         cudaEventDestroy(c->desc_ev[i]);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ss_ctx::kSlots; ++i) {
         if (c->slot[i].d_in) cudaFree(c->slot[i].d_in);
         if (c->slot[i].d_out) cudaFree(c->slot[i].d_out);
         cudaEventDestroy(c->slot[i].ev_in); cudaEventDestroy(c->slot[i].ev_done); cudaEventDestroy(c->slot[i].ev_free);
@@ -570,12 +571,13 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
 }
 
 // split [0, n) into chunks whose spectra fit the L2-sized budget
-static void make_chunks(const ss_ctx* c, const ss_source* items, int n, std::vector<int>& cuts) {
+static void make_chunks(const ss_ctx* c, const ss_source* items, int n, std::vector<int>& cuts, int64_t budget = 0) {
+    if (budget <= 0) budget = c->chunk_bytes;
     cuts.clear(); cuts.push_back(0);
     size_t acc = 0;
     for (int i = 0; i < n; ++i) {
         size_t sb = spectra_bytes(items[i]);
-        if (i > cuts.back() && acc + sb > (size_t)c->chunk_bytes) { cuts.push_back(i); acc = 0; }
+        if (i > cuts.back() && acc + sb > (size_t)budget) { cuts.push_back(i); acc = 0; }
         acc += sb;
     }
     cuts.push_back(n);
@@ -657,14 +659,14 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
         }
     }
     std::vector<int> cuts;
-    make_chunks(c, items, n_items, cuts);
+    make_chunks(c, items, n_items, cuts, c->chunk_bytes_host);
     std::vector<ss_source> dev(n_items);
     std::vector<ss_loud_item> loud;
     std::vector<double*> res_dev(n_items, nullptr);
     int rc = SS_OK;
     for (size_t k = 0; k + 1 < cuts.size() && rc == SS_OK; ++k) {
         const int first = cuts[k], last = cuts[k + 1];
-        ss_ctx::Slot& sl = c->slot[k & 1];
+        ss_ctx::Slot& sl = c->slot[k % ss_ctx::kSlots];
         size_t in_b = 0, out_b = 0;
         for (int i = first; i < last; ++i) {
             const ss_source& it = items[i];
@@ -677,7 +679,7 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
                 out_b += align_up(8 * (size_t)it.C * post[i].n_e, 256) + 256;
             }
         }
-        if (k >= 2) CK(cudaEventSynchronize(sl.ev_free));      // slot's previous chunk fully drained
+        if (k >= (size_t)ss_ctx::kSlots) CK(cudaEventSynchronize(sl.ev_free));      // slot's previous chunk fully drained
         if ((rc = ensure(&sl.d_in, &sl.in_cap, in_b)) != SS_OK) break;
         if ((rc = ensure(&sl.d_out, &sl.out_cap, out_b)) != SS_OK) break;
         char* pi = sl.d_in; char* po = sl.d_out;
