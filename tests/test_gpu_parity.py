@@ -162,3 +162,51 @@ def test_long_rir_partitioned_cfg4_shape_reduced(sm):
     idx, w = so.setup_dynamic_interp(pos, N)
     assert so.rel_rms(sm.convolve_moving_receiver(x, h, idx, w), so.convolve_moving_receiver(x, h, idx, w)) < TOL
     assert so.rel_rms(sm.convolve_fixed_receiver(x[None], h[0]), so.convolve_fixed_receiver(x[None], h[0])) < TOL
+
+
+def test_large_mixed_batch_multi_chunk_two_streams():
+    """Many heterogeneous sources in one device-path call (several chunks, alternating streams, both
+    blocking modes, long RIRs, static sources) == the same sources rendered one by one."""
+    from sonicsim_b200 import render
+    rng = np.random.default_rng(99)
+    R = render.default_renderer()
+    R.set_chunk_bytes(8 << 20)                       # force many chunks
+    try:
+        srcs_np = []
+        for i in range(23):
+            N = int(rng.integers(3000, 90000))
+            C = int(rng.integers(1, 7))
+            kind = i % 4
+            if kind == 0:
+                srcs_np.append(("static", so.synth_dry(rng, N), so.synth_rirs(rng, 1, C, int(rng.integers(8, 3000)))[0]))
+            else:
+                P = int(rng.integers(2, 12))
+                L = int(rng.integers(8, 3000)) if kind != 3 else int(rng.integers(4097, 9000))
+                pos = so.synth_path(rng, P)
+                np.random.seed(i)
+                srcs_np.append(("moving", so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L), render.trajectory_bounds(pos, N)))
+        dev, outs = [], []
+        for s in srcs_np:
+            if s[0] == "static":
+                dev.append(render.StaticSource(torch.from_numpy(s[1]).cuda(), torch.from_numpy(s[2]).cuda()))
+                outs.append(torch.empty((s[2].shape[0], s[1].shape[0]), device="cuda"))
+            else:
+                bh = s[3] if len(dev) % 2 == 0 else None          # mix host-built and device-built block tables
+                dev.append(render.MovingSource(torch.from_numpy(s[1]).cuda(), torch.from_numpy(s[2]).cuda(),
+                                               torch.from_numpy(s[3]).cuda(), bh))
+                outs.append(torch.empty((s[2].shape[1], s[1].shape[0]), device="cuda"))
+        R.render_device(dev, outs)
+        torch.cuda.synchronize()
+        for s, o in zip(srcs_np, outs):
+            if s[0] == "static":
+                one = R.render_host([render.StaticSource(s[1], s[2])])[0]
+                ref = so.convolve_fixed_receiver(s[1][None], s[2])
+            else:
+                one = R.render_host([render.MovingSource(s[1], s[2], s[3])])[0]
+                idx = np.repeat(np.arange(len(s[3]) - 1), np.diff(s[3]))
+                w = np.concatenate([np.linspace(0, 1, n, endpoint=False) for n in np.diff(s[3])]).astype(np.float32)
+                ref = so.convolve_moving_receiver(s[1], s[2], idx, w)
+            assert np.array_equal(o.cpu().numpy(), one)
+            assert so.rel_rms(one, ref) < TOL
+    finally:
+        R.set_chunk_bytes(96 << 20)
