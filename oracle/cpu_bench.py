@@ -27,7 +27,8 @@ _cache = {}
 
 
 def _worker(args):
-    seed, shape, reps = args
+    seed, shape, reps = args[:3]
+    n_samples = args[3] if len(args) > 3 else None
     for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[k] = "1"
     from oracle import sonicsim_oracle as so
@@ -36,6 +37,8 @@ def _worker(args):
         _cache.clear()
         _cache[key] = cfg2_source(seed, *shape)
     x, h, idx, w = _cache[key]
+    if n_samples is not None and n_samples < x.shape[0]:      # bounded sample: the first n_samples of the unit
+        x, idx, w = x[:n_samples], idx[:n_samples], w[:n_samples]
     t0 = time.perf_counter()
     acc = 0.0
     for _ in range(reps):
@@ -70,13 +73,16 @@ class CpuPool:
         self.shape = shape
         self.workers = workers or pick_workers(shape)
         self.pool = mp.get_context("spawn").Pool(self.workers)
-        # warm-up: import scipy, synthesise each worker's unit, run it once
-        self.pool.map(_worker, [(2000 + i, shape, 1) for i in range(self.workers)], chunksize=1)
-
-    def run_batch(self, reps=1):
-        """Every worker renders its unit `reps` times.  Returns (wall seconds, units rendered)."""
+        # warm-up: import scipy, synthesise each worker's unit (untimed), then one timed full-size batch
+        self.pool.map(_worker, [(2000 + i, shape, 1, 4 * shape[2]) for i in range(self.workers)], chunksize=1)
         t0 = time.perf_counter()
-        self.pool.map(_worker, [(2000 + i, self.shape, reps) for i in range(self.workers)], chunksize=1)
+        self.pool.map(_worker, [(2000 + i, shape, 1) for i in range(self.workers)], chunksize=1)
+        self.t_full = time.perf_counter() - t0
+
+    def run_batch(self, reps=1, n_samples=None):
+        """Every worker renders (the first n_samples of) its unit `reps` times.  Returns (wall seconds, units)."""
+        t0 = time.perf_counter()
+        self.pool.map(_worker, [(2000 + i, self.shape, reps, n_samples) for i in range(self.workers)], chunksize=1)
         return time.perf_counter() - t0, self.workers * reps
 
     def close(self):
