@@ -43,3 +43,22 @@ extern thread_local int g_last_cuda;
 
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Take the next slot of the descriptor ring (pinned host block + its device twin), grown to `bytes`.
+// Blocks the host until the slot's previous host->device copy has completed.  The caller fills `*h`,
+// copies it to `*d` on its stream and records c->desc_ev[*slot] right after the copy.
+inline int ring_acquire(ss_ctx* c, size_t bytes, int* slot_out, char** h, char** d) {
+    const int slot = c->ring_pos; c->ring_pos = (c->ring_pos + 1) % ss_ctx::kRing;
+    CK(cudaEventSynchronize(c->desc_ev[slot]));
+    if (bytes > c->desc_cap[slot]) {
+        if (c->h_desc[slot]) CK(cudaFreeHost(c->h_desc[slot]));
+        if (c->d_desc[slot]) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->d_desc[slot])); }
+        c->h_desc[slot] = nullptr; c->d_desc[slot] = nullptr; c->desc_cap[slot] = 0;
+        const size_t cap = align_up(bytes * 2, 4096);
+        CK(cudaHostAlloc((void**)&c->h_desc[slot], cap, cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&c->d_desc[slot], cap));
+        c->desc_cap[slot] = cap;
+    }
+    *slot_out = slot; *h = c->h_desc[slot]; *d = c->d_desc[slot];
+    return SS_OK;
+}

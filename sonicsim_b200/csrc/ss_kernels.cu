@@ -487,19 +487,8 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
             const Shape sh = shape_of(items[i]);
             bytes += align_up(sizeof(Block) * (size_t)sh.nblk_max, 16) + align_up(sizeof(double) * (size_t)items[i].P, 16) + 16;
         }
-    const int slot = c->ring_pos; c->ring_pos = (c->ring_pos + 1) % ss_ctx::kRing;
-    if (bytes > c->desc_cap[slot]) {
-        CK(cudaEventSynchronize(c->desc_ev[slot]));
-        if (c->h_desc[slot]) CK(cudaFreeHost(c->h_desc[slot]));
-        if (c->d_desc[slot]) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->d_desc[slot])); }
-        c->h_desc[slot] = nullptr; c->d_desc[slot] = nullptr; c->desc_cap[slot] = 0;
-        size_t cap = align_up(bytes * 2, 4096);
-        CK(cudaHostAlloc((void**)&c->h_desc[slot], cap, cudaHostAllocDefault));
-        CK(cudaMalloc((void**)&c->d_desc[slot], cap));
-        c->desc_cap[slot] = cap;
-    } else {
-        CK(cudaEventSynchronize(c->desc_ev[slot]));
-    }
+    int slot; char *hblk, *dblk;
+    { int st = ring_acquire(c, bytes, &slot, &hblk, &dblk); if (st) return st; }
     Source* hs = (Source*)c->h_desc[slot];
     int* hps = (int*)(c->h_desc[slot] + off_ps);
     char* scratch = c->d_scratch[buf];

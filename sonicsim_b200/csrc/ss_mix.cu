@@ -146,17 +146,8 @@ extern "C" int ss_mix_dev(ss_ctx* c, const ss_mix_item* items, int n_items, void
         if (a.S > 1 && !a.sirs) return SS_ERR_INVALID;
     }
     const size_t bytes = align_up(sizeof(MixItem) * n_items, 16);
-    const int slot = c->ring_pos; c->ring_pos = (c->ring_pos + 1) % ss_ctx::kRing;
-    CK(cudaEventSynchronize(c->desc_ev[slot]));
-    if (bytes > c->desc_cap[slot]) {
-        if (c->h_desc[slot]) CK(cudaFreeHost(c->h_desc[slot]));
-        if (c->d_desc[slot]) { CK(cudaDeviceSynchronize()); CK(cudaFree(c->d_desc[slot])); }
-        c->h_desc[slot] = nullptr; c->d_desc[slot] = nullptr; c->desc_cap[slot] = 0;
-        size_t cap = align_up(bytes * 2, 4096);
-        CK(cudaHostAlloc((void**)&c->h_desc[slot], cap, cudaHostAllocDefault));
-        CK(cudaMalloc((void**)&c->d_desc[slot], cap));
-        c->desc_cap[slot] = cap;
-    }
+    int slot; char *hblk, *dblk;
+    { int st = ring_acquire(c, bytes, &slot, &hblk, &dblk); if (st) return st; }
     MixItem* h = (MixItem*)c->h_desc[slot];
     for (int i = 0; i < n_items; ++i) {
         const ss_mix_item& a = items[i];
