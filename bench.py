@@ -254,9 +254,10 @@ def run_ours(args, rank, local_rank, world):
         alg_per_launch = step_alg * K / max(n_pairs, 1)
         achieved = alg_per_launch / k_render_s / 1e9 if k_render_s > 0 else 0.0
         achieved_path = step_alg * K / dev_s / 1e9              # whole hot path over the timed region itself
-        traffic, traffic_note = None, "no ncu capture found (profiles/ncu_traffic.json)"
+        traffic, traffic_note, ncu_extra = None, "no ncu capture found (profiles/ncu_traffic.json)", None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ncu_extra = {k: tj["k_render"].get(k) for k in ("issue_slots_busy_pct", "fma_pipe_active_pct", "dram_pct_of_peak")}
             per_src = (tj["k_render"]["dram_read_mb"] + tj["k_render"]["dram_write_mb"]) * 1e6 / tj["sources_per_launch"]
             traffic = per_src * (n_src * K / max(n_pairs, 1))
             traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one k_render launch from `ncu --set full` "
@@ -282,6 +283,7 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                          "limiter": "fp32 issue + shared-memory/barrier latency, not DRAM (see DESIGN.md section 4)",
+                         "ncu_k_render": ncu_extra,
                          "alg_bytes_per_launch": alg_per_launch, "kernel_ms": 1e3 * k_render_s,
                          "k_prepare_ms": 1e3 * k_spec_s, "path_achieved": achieved_path,
                          "path_frac": achieved_path / peak, "launch_pairs_timed": int(n_pairs),

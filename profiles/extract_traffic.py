@@ -20,6 +20,10 @@ def metrics(path):
         v, u = float(d[key]), units[key]
         return v * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}[u]
     return {"kernel": d.get("Kernel Name", "?"), "grid": d.get("launch__grid_size"),
+            "issue_slots_busy_pct": float(d["sm__inst_issued.avg.pct_of_peak_sustained_active"]),
+            "fma_pipe_active_pct": float(d["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]),
+            "warp_instructions": float(d["smsp__inst_executed.sum"]),
+            "dram_pct_of_peak": float(d["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]),
             "dram_read_mb": mb("dram__bytes_read.sum"), "dram_write_mb": mb("dram__bytes_write.sum"),
             "duration_us_under_ncu": float(d["gpu__time_duration.sum"])}
 
