@@ -12,6 +12,8 @@
  *     void*; NULL = legacy default stream) without synchronising.
  *   - `*_host` entry points take HOST pointers (pinned memory gives full PCIe rate), copy in,
  *     render and copy out; they return after the results are in host memory.
+ *   - an ss_ctx is NOT thread-safe: use one context per host thread (one process per GPU is the
+ *     intended deployment); calls on one context are serialised by the caller.
  *   - every function returns 0 (SS_OK) or a negative ss_status; ss_strerror() describes it.  The
  *     Python shim turns these into the exception types the reference raises (IndexError /
  *     ValueError), see INTEGRATION.md.
