@@ -421,10 +421,30 @@ static int validate_item(const ss_source& it) {
 }
 // shapes derived from one ss_source
 struct Shape { int K, nb, aligned, nblk_max, per, max_items; };
+// Aligned blocking costs one transform per block, sum_s ceil(n_s / 4096); grid blocking costs
+// ceil(positions touched / 2) per 4096-block.  With the bounds on the host both counts are exact and the
+// cheaper plan wins (trajectories with many short segments are better off on the grid); without them the
+// plan is aligned when the average segment is at least one block long.
+static bool choose_aligned(const ss_source& it, int K, int nb) {
+    if (it.mode != SS_MOVING_BOUNDS || K != 1) return false;
+    const int32_t* hb = it.bounds_host;
+    if (!hb) return (int64_t)(it.P - 1) * kB <= (int64_t)it.N;
+    int64_t aligned = 0, grid = 0;
+    for (int sg = 0; sg + 1 < it.P; ++sg) aligned += seg_blocks(hb[sg + 1] - hb[sg]);
+    int lo = 0;                                          // first segment that reaches into the current block
+    for (int b = 0; b < nb; ++b) {
+        const int n0 = b * kB, n1 = (n0 + kB < it.N ? n0 + kB : it.N) - 1;
+        while (lo + 2 < it.P && hb[lo + 1] <= n0) ++lo;
+        int hi = lo;
+        while (hi + 2 < it.P && hb[hi + 1] <= n1) ++hi;
+        grid += (hi - lo + 2 + 1) / 2;                   // positions lo .. hi + 1, two per transform
+    }
+    return aligned <= grid;
+}
 static Shape shape_of(const ss_source& it) {
     Shape s;
     s.K = (it.L + kB - 1) / kB; s.nb = (it.N + kB - 1) / kB;
-    s.aligned = (it.mode == SS_MOVING_BOUNDS && s.K == 1) ? 1 : 0;
+    s.aligned = choose_aligned(it, s.K, s.nb) ? 1 : 0;
     s.nblk_max = s.aligned ? s.nb + it.P - 1 : s.nb;
     s.per = it.mode == SS_STATIC ? (it.C + 1) / 2 : it.C;
     s.max_items = s.nblk_max * s.per;

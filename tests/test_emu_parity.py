@@ -44,7 +44,7 @@ def test_golden_moving_both_trajectory_forms(emu, golden):
 
 
 @pytest.mark.parametrize("P,C,L,N", [(3, 1, 1, 100), (2, 2, 4096, 4096), (2, 1, 4097, 8193), (9, 3, 600, 12289),
-                                     (5, 2, 9000, 5000)])
+                                     (5, 2, 9000, 5000), (60, 2, 300, 9000)])
 def test_shapes_and_partitions(emu, P, C, L, N):
     rng = np.random.default_rng(P * 1000 + L)
     x, h, pos = so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L), so.synth_path(rng, P)
@@ -52,6 +52,7 @@ def test_shapes_and_partitions(emu, P, C, L, N):
     idx, w = so.setup_dynamic_interp(pos, N)
     ref = so.convolve_moving_exact_f64(x, h, idx, w)
     assert so.rel_rms(emu.render(x, h, idx=idx, w=w, mode=2), ref) < 5e-6
+    assert so.rel_rms(emu.render(x, h, bounds=bounds_of(idx, P), mode=1), ref) < 5e-6
 
 
 def test_zero_length_segments_and_n_lt_segments(emu):

@@ -60,7 +60,8 @@ def test_golden_interpolate_moving_audio(sm, golden):
 
 
 @pytest.mark.parametrize("P,C,L,N", [(3, 1, 1, 100), (2, 2, 4096, 4096), (2, 1, 4097, 8193), (9, 3, 600, 12289),
-                                     (5, 2, 9000, 5000), (40, 6, 4096, 100000), (13, 5, 257, 70001)])
+                                     (5, 2, 9000, 5000), (40, 6, 4096, 100000), (13, 5, 257, 70001),
+                                     (200, 2, 300, 50000)])          # many short segments: the grid plan is chosen
 def test_shapes_and_partitions(sm, P, C, L, N):
     rng = np.random.default_rng(P * 1000 + L)
     x, h, pos = so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L), so.synth_path(rng, P)
@@ -68,6 +69,11 @@ def test_shapes_and_partitions(sm, P, C, L, N):
     idx, w = so.setup_dynamic_interp(pos, N)
     ref = so.convolve_moving_receiver(x, h, idx, w)
     assert so.rel_rms(sm.convolve_moving_receiver(x, h, idx, w), ref) < TOL
+    # compact-trajectory form of the same render (aligned or grid blocking, whichever is cheaper)
+    from sonicsim_b200 import render
+    bounds = np.concatenate([[0], np.cumsum(np.bincount(idx, minlength=P - 1))]).astype(np.int32)
+    y = render.default_renderer().render_host([render.MovingSource(x, h, bounds)])[0]
+    assert so.rel_rms(y, ref) < TOL
 
 
 def test_empty_segments_ragged_and_random_indices(sm):
