@@ -103,3 +103,35 @@ def test_known_answers(emu):
     ym = emu.render(x, h2, idx=idx2, w=w2, mode=2)
     ys = emu.render(x, h1[0], mode=0)
     assert so.rel_rms(ym, ys) < 2e-6
+
+
+def test_randomised_shapes_around_block_edges(emu):
+    """Random shapes biased towards the block / partition edges (4095, 4096, 4097, 8191, ...), both
+    trajectory forms and the static path, against the float64 ground truth."""
+    rng = np.random.default_rng(2024)
+    edges = [1, 2, 255, 256, 257, 4095, 4096, 4097, 8191, 8192, 8193, 12288]
+    for case in range(14):
+        N = int(rng.choice(edges)) + int(rng.integers(0, 3)) * int(rng.choice([0, 1, 17, 4096]))
+        L = int(rng.choice([1, 2, 31, 4095, 4096, 4097, 6000]))
+        C = int(rng.integers(1, 4))
+        P = int(rng.integers(2, 7))
+        N = max(N, P)                                   # at least one sample per ... not required, but keeps counts >= 0
+        x = so.synth_dry(rng, N)
+        h = rng.standard_normal((P, C, L)).astype(np.float32) * np.exp(-np.arange(L) / max(L / 4, 1)).astype(np.float32)
+        pos = so.synth_path(rng, P)
+        idx = w = None
+        for seed in range(30):
+            np.random.seed(seed)
+            try:
+                idx, w = so.setup_dynamic_interp(pos, N)
+                break
+            except ValueError:
+                continue
+        if idx is None:
+            continue
+        ref = so.convolve_moving_exact_f64(x, h, idx, w)
+        tol = 2e-5 if np.sqrt(np.mean(ref ** 2)) > 1e-6 else 1.0
+        assert so.rel_rms(emu.render(x, h, idx=idx, w=w, mode=2), ref) < tol, (case, N, L, C, P)
+        assert so.rel_rms(emu.render(x, h, bounds=bounds_of(idx, P), mode=1), ref) < tol, (case, N, L, C, P)
+        refs = so.convolve_fixed_receiver(x.astype(np.float64)[None], h[0].astype(np.float64))
+        assert so.rel_rms(emu.render(x, h[0], mode=0), refs) < tol, (case, N, L, C)
