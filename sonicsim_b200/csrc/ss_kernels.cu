@@ -582,12 +582,24 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
 // split [0, n) into chunks whose spectra fit the L2-sized budget
 static void make_chunks(const ss_ctx* c, const ss_source* items, int n, std::vector<int>& cuts, int64_t budget = 0) {
     if (budget <= 0) budget = c->chunk_bytes;
-    cuts.clear(); cuts.push_back(0);
-    size_t acc = 0;
+    // greedy pass: how many chunks does the budget need ...
+    std::vector<size_t> sb(n);
+    size_t total = 0, acc = 0;
+    int n_chunks = 1;
     for (int i = 0; i < n; ++i) {
-        size_t sb = spectra_bytes(items[i]);
-        if (i > cuts.back() && acc + sb > (size_t)budget) { cuts.push_back(i); acc = 0; }
-        acc += sb;
+        sb[i] = spectra_bytes(items[i]);
+        total += sb[i];
+        if (acc > 0 && acc + sb[i] > (size_t)budget) { ++n_chunks; acc = 0; }
+        acc += sb[i];
+    }
+    // ... then cut at equal shares of the total, so that the last chunk is not a runt (7,7,7,7,4 -> 6,6,7,6,7):
+    // equal chunks keep both streams of the overlap equally busy
+    cuts.clear(); cuts.push_back(0);
+    acc = 0;
+    for (int i = 0; i < n; ++i) {
+        const size_t target = total * cuts.size() / n_chunks;
+        if (i > cuts.back() && (acc + sb[i] / 2 > target || acc - (cuts.size() > 1 ? total * (cuts.size() - 1) / n_chunks : 0) + sb[i] > (size_t)budget)) cuts.push_back(i);
+        acc += sb[i];
     }
     cuts.push_back(n);
 }

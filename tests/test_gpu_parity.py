@@ -203,7 +203,7 @@ def test_large_mixed_batch_multi_chunk_two_streams():
                 outs.append(torch.empty((s[2].shape[1], s[1].shape[0]), device="cuda"))
         R.render_device(dev, outs)
         torch.cuda.synchronize()
-        for s, o in zip(srcs_np, outs):
+        for s, o, dsrc in zip(srcs_np, outs, dev):
             if s[0] == "static":
                 one = R.render_host([render.StaticSource(s[1], s[2])])[0]
                 ref = so.convolve_fixed_receiver(s[1][None], s[2])
@@ -212,7 +212,11 @@ def test_large_mixed_batch_multi_chunk_two_streams():
                 idx = np.repeat(np.arange(len(s[3]) - 1), np.diff(s[3]))
                 w = np.concatenate([np.linspace(0, 1, n, endpoint=False) for n in np.diff(s[3])]).astype(np.float32)
                 ref = so.convolve_moving_receiver(s[1], s[2], idx, w)
-            assert np.array_equal(o.cpu().numpy(), one)
+            same_plan = s[0] == "static" or dsrc.bounds_host is not None      # without host bounds the blocking plan is a heuristic
+            if same_plan:
+                assert np.array_equal(o.cpu().numpy(), one)
+            else:
+                assert so.rel_rms(o.cpu().numpy(), one) < 2e-6
             assert so.rel_rms(one, ref) < TOL
     finally:
         R.set_chunk_bytes(96 << 20)
