@@ -183,3 +183,52 @@ def render_scene(moving: T.Sequence[T.Tuple], static: T.Sequence[T.Tuple] = (), 
             targets.append(None if l is None else np.random.uniform(l - 2, l + 2))
     outs = default_renderer().render_host(srcs, lufs_targets=targets, sr=sr)
     return outs[: len(moving)], outs[len(moving):]
+
+
+def render_mixtures(utterances: T.Sequence[dict], device: T.Optional[int] = None) -> T.List[dict]:
+    """Whole path on the device, per utterance: render every speaker / noise stem, then assemble the training
+    mixture exactly as the dataloader does (separation/look2hear/datas/movingdatamodule.py:105-124) without the
+    stems leaving HBM.  Additive API (torch is used for device memory and copies only).
+
+    utterance = {"speakers": [(dry (N,), rirs (P, C, L), positions (P, 3)), ...],     # speaker 0 is the reference
+                 "noises":   [(dry (N,), rir (C, L)), ...],
+                 "sirs": (S-1,) dB, "snr": dB}
+    Returns per utterance {"mix": (C, N) float32, "speakers": (S, C, N) float32 (after their gains)}.
+    Every stem of an utterance must have the same (C, N)."""
+    import torch
+    from ._lib import SsMixItem
+    R = default_renderer() if device is None else Renderer(device)
+    dev = torch.device("cuda", R.device if R.device is not None else torch.cuda.current_device())
+    lib = R.lib
+    srcs, outs, plan = [], [], []
+    for u in utterances:
+        S, M = len(u["speakers"]), len(u["noises"])
+        N = int(np.asarray(u["speakers"][0][0]).shape[-1])
+        C = int(np.asarray(u["speakers"][0][1]).shape[1])
+        spk = torch.empty((S, C, N), dtype=torch.float32, device=dev)
+        noi = torch.empty((M, C, N), dtype=torch.float32, device=dev)
+        for i, (d, h, pos) in enumerate(u["speakers"]):
+            b = trajectory_bounds(pos, N)
+            srcs.append(MovingSource(torch.from_numpy(_as_f32(d).reshape(-1)).to(dev), torch.from_numpy(_as_f32(h)).to(dev),
+                                     torch.from_numpy(b).to(dev), b))
+            outs.append(spk[i])
+        for i, (d, h) in enumerate(u["noises"]):
+            srcs.append(StaticSource(torch.from_numpy(_as_f32(d).reshape(-1)).to(dev), torch.from_numpy(_as_f32(h)).to(dev)))
+            outs.append(noi[i])
+        plan.append((spk, noi, S, M, C, N, u))
+    R.render_device(srcs, outs)
+    n = len(plan)
+    items = (SsMixItem * n)()
+    keep = []
+    nscr = int(lib.ss_mix_scratch_doubles())
+    for k, (spk, noi, S, M, C, N, u) in enumerate(plan):
+        mix = torch.empty((C, N), dtype=torch.float32, device=dev)
+        sirs = torch.tensor(np.asarray(u.get("sirs", np.zeros(max(S - 1, 1))), dtype=np.float32).reshape(-1), device=dev)
+        scr = torch.empty(nscr, dtype=torch.float64, device=dev)
+        items[k] = SsMixItem(speakers=spk.data_ptr(), noises=noi.data_ptr(), sirs=sirs.data_ptr(), mix=mix.data_ptr(),
+                             speakers_out=spk.data_ptr(), scratch=scr.data_ptr(), E=C * N, S=S, M=M,
+                             snr=float(np.asarray(u.get("snr", 15.0)).reshape(-1)[0]))
+        keep.append((mix, sirs, scr))
+    _lib.check(lib.ss_mix_dev(R.ctx, items, n, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    return [{"mix": keep[k][0].cpu().numpy(), "speakers": plan[k][0].cpu().numpy()} for k in range(n)]
