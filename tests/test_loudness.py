@@ -121,3 +121,19 @@ def test_gpu_render_scene_with_loudness_matches_reference_pipeline():
         refs.append(so.get_lufs_norm_audio(np.ascontiguousarray(stem.T), 16000, l)[0].T)
     for y, r in zip(ym + ys, refs):
         assert so.rel_rms(y, r) < 1e-4
+
+
+def test_relative_gate_known_answer(emu):
+    """BS.1770 gating, analytic expectation: 10 s of a 997 Hz sine at -20 dBFS followed by 10 s at -50 dBFS.
+    Both halves pass the absolute gate (-70); their mean power sets the relative gate at about -36 LKFS, which
+    removes the quiet half: the integrated loudness is that of the loud half, -23.0 LKFS."""
+    sr = 48000
+    t = np.arange(sr * 10) / sr
+    sine = np.sin(2 * np.pi * 997 * t)
+    x = np.concatenate([sine * 10 ** (-20 / 20), sine * 10 ** (-50 / 20)]).astype(np.float32)
+    ref = so.bs1770_integrated_loudness(x, sr)
+    assert abs(ref - (-23.01)) < 0.08
+    got, _ = emu.lufs(x, sr, 0.4)
+    assert abs(got - ref) < 1e-4
+    # without the relative gate the answer would be the mean power of both halves, ~ -26.0: the gate matters
+    assert ref > -24.0
