@@ -273,23 +273,38 @@ __host__ __device__ __noinline__
 #endif
 inline void form_z_parts(int t, const XDesc& d, float2* Ra, float2* Rb) {
     const int jB = passA_jB(t);
-    for (int part = 1; part < d.kparts; ++part) {
+    float2 a[16], b[16];                       // accumulators in registers for the duration of the call
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a[i] = Ra[i]; b[i] = Rb[i]; }
+    const int kparts = d.kparts;
+    const bool has_q = d.Hq != nullptr;
+    for (int part = 1; part < kparts; ++part) {
         const float2* xa_p = d.X - (size_t)part * kSpec + t;
         const float2* xb_p = d.X - (size_t)part * kSpec + jB;
         const float2* ha_p = d.Hp + (size_t)part * kSpec + t;
         const float2* hb_p = d.Hp + (size_t)part * kSpec + jB;
-        const float2* ga_p = d.Hq ? d.Hq + (size_t)part * kSpec + t : nullptr;
-        const float2* gb_p = d.Hq ? d.Hq + (size_t)part * kSpec + jB : nullptr;
-        for (int m = 0; m < 8; ++m) {
-            float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
-            cmac(Ra[m], xa, ldg_stream(ha_p + 512 * m));
-            cmac(Rb[m], xb, ldg_stream(hb_p + 512 * m));
-            if (ga_p) {
-                cmac(Rb[15 - m], xa, ldg_stream(ga_p + 512 * m));
-                cmac(Ra[15 - m], xb, ldg_stream(gb_p + 512 * m));
+        if (has_q) {
+            const float2* ga_p = d.Hq + (size_t)part * kSpec + t;
+            const float2* gb_p = d.Hq + (size_t)part * kSpec + jB;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
+                cmac(a[m], xa, ldg_stream(ha_p + 512 * m));
+                cmac(b[m], xb, ldg_stream(hb_p + 512 * m));
+                cmac(b[15 - m], xa, ldg_stream(ga_p + 512 * m));
+                cmac(a[15 - m], xb, ldg_stream(gb_p + 512 * m));
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
+                cmac(a[m], xa, ldg_stream(ha_p + 512 * m));
+                cmac(b[m], xb, ldg_stream(hb_p + 512 * m));
             }
         }
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { Ra[i] = a[i]; Rb[i] = b[i]; }
 }
 
 // Z formation fused with pass A.  sX / sHp / sHq: partition 0 of the dry window and of the two
