@@ -267,15 +267,11 @@ SS_HD void spectra_phase4(int t, const float2* s, const Row& ra, const Row& rb) 
 // =======================================================================================
 
 // RIR partitions >= 1 (long RIRs only), streamed from global memory and accumulated into the
-// (P_A, P_B, Q_A, Q_B) slots of form_z.  Out of line on purpose: it keeps the K = 1 fast path small.
-#if defined(__CUDACC__)
-__host__ __device__ __noinline__
-#endif
-inline void form_z_parts(int t, const XDesc& d, float2* Ra, float2* Rb) {
+// (P_A, P_B, Q_A, Q_B) slots of form_z.  Only instantiated in the LONG variant of k_render, which is
+// launched for chunks that contain a source with L > 4096: keeping this loop (or even a call to it) out
+// of the common kernel is worth 9 % there (register allocation of the hot loop).
+SS_HD void form_z_parts(int t, const XDesc& d, Regs32& R) {
     const int jB = passA_jB(t);
-    float2 a[16], b[16];                       // accumulators in registers for the duration of the call
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { a[i] = Ra[i]; b[i] = Rb[i]; }
     const int kparts = d.kparts;
     const bool has_q = d.Hq != nullptr;
     for (int part = 1; part < kparts; ++part) {
@@ -289,28 +285,27 @@ inline void form_z_parts(int t, const XDesc& d, float2* Ra, float2* Rb) {
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
-                cmac(a[m], xa, ldg_stream(ha_p + 512 * m));
-                cmac(b[m], xb, ldg_stream(hb_p + 512 * m));
-                cmac(b[15 - m], xa, ldg_stream(ga_p + 512 * m));
-                cmac(a[15 - m], xb, ldg_stream(gb_p + 512 * m));
+                cmac(R.a[m], xa, ldg_stream(ha_p + 512 * m));
+                cmac(R.b[m], xb, ldg_stream(hb_p + 512 * m));
+                cmac(R.b[15 - m], xa, ldg_stream(ga_p + 512 * m));
+                cmac(R.a[15 - m], xb, ldg_stream(gb_p + 512 * m));
             }
         } else {
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 float2 xa = ldg_stream(xa_p + 512 * m), xb = ldg_stream(xb_p + 512 * m);
-                cmac(a[m], xa, ldg_stream(ha_p + 512 * m));
-                cmac(b[m], xb, ldg_stream(hb_p + 512 * m));
+                cmac(R.a[m], xa, ldg_stream(ha_p + 512 * m));
+                cmac(R.b[m], xb, ldg_stream(hb_p + 512 * m));
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { Ra[i] = a[i]; Rb[i] = b[i]; }
 }
 
 // Z formation fused with pass A.  sX / sHp / sHq: partition 0 of the dry window and of the two
 // real filters packed into this transform, staged in shared memory (linear, 4096 words each) by the
 // bulk-copy engine; sHq may be null.  RIR partitions j >= 1 (long RIRs) pair with the dry window
 // 4096 j samples earlier (grid blocking) and are streamed from global memory through `d`.
+template <bool LONG>
 SS_HD void form_z(int t, const float2* sX, const float2* sHp, const float2* sHq, const XDesc& d, Regs32& R) {
     const int jB = passA_jB(t);
     {
@@ -336,15 +331,8 @@ SS_HD void form_z(int t, const float2* sX, const float2* sHp, const float2* sHq,
             }
         }
     }
-    const int kparts = d.kparts;
-    if (kparts > 1) {
-        float2 ta[16], tb[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { ta[i] = R.a[i]; tb[i] = R.b[i]; }
-        form_z_parts(t, d, ta, tb);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { R.a[i] = ta[i]; R.b[i] = tb[i]; }
-    }
+    const int kparts = LONG ? d.kparts : 1;
+    if (LONG) form_z_parts(t, d, R);
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
         float2 PA = R.a[m], QA = R.b[15 - m], PB = R.b[m], QB = R.a[15 - m];

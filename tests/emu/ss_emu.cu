@@ -127,7 +127,7 @@ static void cta_render(const RItem* items, int n_items, int cta, int grid, const
     for (int k = 0;; ++k) {
         const XDesc& d = s_desc[k & 1];
         if (!d.valid) break;
-        for (int t = 0; t < kThreads; ++t) form_z(t, sX, sHp, d.Hq ? sHq : nullptr, d, R[t]);
+        for (int t = 0; t < kThreads; ++t) form_z<true>(t, sX, sHp, d.Hq ? sHq : nullptr, d, R[t]);
         {   // thread 0: publish transform k+1, stage its Hq
             XDesc nx; memset(&nx, 0, sizeof(nx));
             const RItem& cur = s_item[slot];
