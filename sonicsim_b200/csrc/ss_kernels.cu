@@ -189,7 +189,9 @@ constexpr int kRenderSmem = kPadF * (int)sizeof(float2) + kSpecBytes;         //
 // while the CTA computes transform k it has the bulk-copy engine stage transform k+1's spectra —
 // Hq into the staging buffer as soon as form_z(k) has consumed it, X and Hp into the FFT buffer itself
 // once pass C of transform k has read it out — so form_z never waits on L2.
-template <bool LONG>
+// LONG: RIR partitions >= 1 are accumulated (L > 4096).  FAST: every item of the chunk is a compact-trajectory
+// source under aligned blocking (one transform per block, two positions each, one segment per block).
+template <bool LONG, bool FAST>
 __global__ void __launch_bounds__(kThreads, SS_RENDER_MINB)
 k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr) {
     extern __shared__ __align__(128) float2 smem[];
@@ -238,7 +240,7 @@ k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr) {
         mbar_wait(&s_bar[1], k & 1);
         const XDesc& d = s_desc[k & 1];
         if (!d.valid) break;
-        form_z<LONG>(t, sX, sHp, d.Hq ? sHq : nullptr, d, R);
+        form_z<LONG, FAST>(t, sX, sHp, (FAST || d.Hq) ? sHq : nullptr, d, R);
         __syncthreads();                              // staged spectra consumed, s_desc[k & 1] read by all
         if (t == 0) {
             // publish transform k+1 and start staging its Hq
@@ -275,7 +277,7 @@ k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr) {
             } else mbar_arrive(&s_bar[0]);
         }
         render_phase3(t, R, T);
-        render_epilogue(t, d, R);
+        render_epilogue<FAST>(t, d, R);
     }
 }
 
@@ -325,8 +327,9 @@ extern "C" int ss_create(int device, ss_ctx** out) {
     CK(cudaMemcpyToSymbol(g_twB, tb.data(), sizeof(float2) * kTabB));
     CK(cudaMemcpyToSymbol(g_twC, tc.data(), sizeof(float2) * kTabC));
     CK(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
-    CK(cudaFuncSetAttribute(k_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
-    CK(cudaFuncSetAttribute(k_render<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
+    CK(cudaFuncSetAttribute(k_render<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
+    CK(cudaFuncSetAttribute(k_render<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
+    CK(cudaFuncSetAttribute(k_render<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
     for (int i = 0; i < ss_ctx::kRing; ++i) CK(cudaEventCreateWithFlags(&c->desc_ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         CK(cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking));
@@ -574,10 +577,11 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
     CK(cudaGetLastError());
     if (c->profiling) CK(cudaEventRecord(pf.e1, stream));
     const int grid_r = pr < c->sm_count * SS_RENDER_MINB ? pr : c->sm_count * SS_RENDER_MINB;
-    bool any_long = false;
-    for (int i = first; i < last; ++i) any_long = any_long || items[i].L > kB;
-    if (any_long) k_render<true><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total);
-    else k_render<false><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total);
+    bool any_long = false, all_aligned = true;
+    for (int i = 0; i < n; ++i) { any_long = any_long || hs[i].K > 1; all_aligned = all_aligned && hs[i].aligned; }
+    if (any_long) k_render<true, false><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total);
+    else if (all_aligned && !getenv("SS_NO_FAST")) k_render<false, true><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total);
+    else k_render<false, false><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total);
     CK(cudaGetLastError());
     if (c->profiling) { CK(cudaEventRecord(pf.e2, stream)); c->prof.push_back(pf); }
     c->launches += 2;

@@ -305,12 +305,12 @@ SS_HD void form_z_parts(int t, const XDesc& d, Regs32& R) {
 // real filters packed into this transform, staged in shared memory (linear, 4096 words each) by the
 // bulk-copy engine; sHq may be null.  RIR partitions j >= 1 (long RIRs) pair with the dry window
 // 4096 j samples earlier (grid blocking) and are streamed from global memory through `d`.
-template <bool LONG>
+template <bool LONG, bool FAST = false>
 SS_HD void form_z(int t, const float2* sX, const float2* sHp, const float2* sHq, const XDesc& d, Regs32& R) {
     const int jB = passA_jB(t);
     {
         const float2 *xa_p = sX + t, *xb_p = sX + jB, *ha_p = sHp + t, *hb_p = sHp + jB;
-        if (sHq) {
+        if (FAST || sHq) {          // FAST: every transform packs two positions (aligned blocking)
             const float2 *ga_p = sHq + t, *gb_p = sHq + jB;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
@@ -343,7 +343,7 @@ SS_HD void form_z(int t, const float2* sX, const float2* sHp, const float2* sHq,
         // thread 0 owns the self-mirrored butterflies 0 and 256 and the packed (DC, Nyquist) word
         float2 x0 = sX[0], h0 = sHp[0];
         float pdc = x0.x * h0.x, pny = x0.y * h0.y, qdc = 0.f, qny = 0.f;
-        if (sHq) { float2 g0 = sHq[0]; qdc = x0.x * g0.x; qny = x0.y * g0.y; }
+        if (FAST || sHq) { float2 g0 = sHq[0]; qdc = x0.x * g0.x; qny = x0.y * g0.y; }
         for (int part = 1; part < kparts; ++part) {
             x0 = (d.X - (size_t)part * kSpec)[0];
             h0 = (d.Hp + (size_t)part * kSpec)[0];
@@ -390,6 +390,7 @@ SS_HD void hat_pair(int sg, float w, int p, float& fa, float& fb) {
 // transform of its block (plain store); the second transform of a block that straddles a waypoint
 // (grid blocking only) accumulates with a fire-and-forget RED - two addends per address, the first
 // stored by this very thread, so the sum is order-free.
+template <bool FAST = false>
 SS_HD void render_epilogue(int t, const XDesc& d, const Regs32& R) {
     // `d` lives in shared memory: copy what the loop needs into registers once - after every global
     // store the compiler would otherwise have to reload each field (generic pointers may alias)
@@ -397,7 +398,7 @@ SS_HD void render_epilogue(int t, const XDesc& d, const Regs32& R) {
     float* const row = d.row;
     const bool first = d.first != 0;
     if (nbase >= n_end) return;
-    if (mode == MODE_STATIC) {                               // Re -> channel c, Im -> channel c + 1
+    if (!FAST && mode == MODE_STATIC) {                      // Re -> channel c, Im -> channel c + 1
         float* const row1 = d.row1;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -408,7 +409,7 @@ SS_HD void render_epilogue(int t, const XDesc& d, const Regs32& R) {
                 if (row1) row1[n] = z.y;
             }
         }
-    } else if (mode == MODE_MOVING_BOUNDS && d.p_lo + 1 == d.p_hi) {
+    } else if (FAST || (mode == MODE_MOVING_BOUNDS && d.p_lo + 1 == d.p_hi)) {
         // the block lies inside one segment (always so under aligned blocking): sg = p for every
         // sample, 16 independent weight computations, lerp = (1 - w) Re z + w Im z
         const int b0 = d.bounds[p];

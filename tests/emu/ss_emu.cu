@@ -99,7 +99,7 @@ static void prepare_ranges(const Source& S, RItem* items) {
 
 // One persistent k_render CTA (`cta` of `grid`): same control flow as the kernel; the bulk copies
 // are done at the point where thread 0 issues them, the mbarrier waits are no-ops.
-static void cta_render(const RItem* items, int n_items, int cta, int grid, const Tables& T) {
+static void cta_render(const RItem* items, int n_items, int cta, int grid, const Tables& T, bool fast) {
     std::vector<float2> smem(kPadF + kSpec);
     std::vector<Regs32> R(kThreads);
     float2* const fftbuf = smem.data();
@@ -127,7 +127,10 @@ static void cta_render(const RItem* items, int n_items, int cta, int grid, const
     for (int k = 0;; ++k) {
         const XDesc& d = s_desc[k & 1];
         if (!d.valid) break;
-        for (int t = 0; t < kThreads; ++t) form_z<true>(t, sX, sHp, d.Hq ? sHq : nullptr, d, R[t]);
+        for (int t = 0; t < kThreads; ++t) {
+            if (fast) form_z<false, true>(t, sX, sHp, sHq, d, R[t]);          // k_render<false, true>
+            else form_z<true, false>(t, sX, sHp, d.Hq ? sHq : nullptr, d, R[t]);   // k_render<true, false> covers <false, false> too
+        }
         {   // thread 0: publish transform k+1, stage its Hq
             XDesc nx; memset(&nx, 0, sizeof(nx));
             const RItem& cur = s_item[slot];
@@ -152,7 +155,7 @@ static void cta_render(const RItem* items, int n_items, int cta, int grid, const
         }
         for (int t = 0; t < kThreads; ++t) {
             render_phase3(t, R[t], T);
-            render_epilogue(t, dcur, R[t]);
+            if (fast) render_epilogue<true>(t, dcur, R[t]); else render_epilogue<false>(t, dcur, R[t]);
         }
     }
 }
@@ -181,7 +184,7 @@ int emu_render(const float* x, const float* rir, float* out, const int32_t* boun
     prepare_ranges(S, items.data());
     const int nr = counts[0] * items_per_block(S);
     const int grid = nr < 3 ? nr : 3;              // a few persistent CTAs, each looping over many items
-    for (int cta = 0; cta < grid; ++cta) cta_render(items.data(), nr, cta, grid, T);
+    for (int cta = 0; cta < grid; ++cta) cta_render(items.data(), nr, cta, grid, T, S.aligned != 0);
     return 0;
 }
 
