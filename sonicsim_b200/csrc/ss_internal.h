@@ -12,16 +12,20 @@ struct ss_ctx {
     int64_t chunk_bytes = 96ll << 20;        // device path: launch granularity (bigger = better amortised)
     int64_t chunk_bytes_host = 28ll << 20;   // host path: copy/compute/copy pipeline granularity (PCIe-bound)
     // scratch for spectra
-    // two scratch buffers: consecutive chunks of ss_render_dev alternate between them (and between two
+    // kAux scratch buffers: consecutive chunks of ss_render_dev rotate through them (and through as many
     // internal streams) so that chunk i+1's descriptor copy + k_prepare overlap chunk i's k_render tail
-    char* d_scratch[2] = {nullptr, nullptr}; size_t scratch_cap[2] = {0, 0};
-    cudaStream_t s_aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+#ifndef SS_AUX_STREAMS
+#define SS_AUX_STREAMS 3
+#endif
+    static const int kAux = SS_AUX_STREAMS;
+    char* d_scratch[kAux] = {}; size_t scratch_cap[kAux] = {};
+    cudaStream_t s_aux[kAux] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
     // descriptor ring (pinned host + device)
-    static const int kRing = 4;
-    char* h_desc[kRing] = {nullptr, nullptr, nullptr, nullptr};
-    char* d_desc[kRing] = {nullptr, nullptr, nullptr, nullptr};
-    size_t desc_cap[kRing] = {0, 0, 0, 0};
+    static const int kRing = 2 * SS_AUX_STREAMS;      // multiple of kAux: a slot is always reused on the same stream
+    char* h_desc[kRing] = {};
+    char* d_desc[kRing] = {};
+    size_t desc_cap[kRing] = {};
     cudaEvent_t desc_ev[kRing];
     int ring_pos = 0;
     // host path

@@ -331,7 +331,7 @@ extern "C" int ss_create(int device, ss_ctx** out) {
     CK(cudaFuncSetAttribute(k_render<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
     CK(cudaFuncSetAttribute(k_render<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
     for (int i = 0; i < ss_ctx::kRing; ++i) CK(cudaEventCreateWithFlags(&c->desc_ev[i], cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ss_ctx::kAux; ++i) {
         CK(cudaStreamCreateWithFlags(&c->s_aux[i], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
@@ -354,7 +354,7 @@ extern "C" void ss_destroy(ss_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ss_ctx::kAux; ++i) {
         if (c->d_scratch[i]) cudaFree(c->d_scratch[i]);
         if (c->s_aux[i]) cudaStreamDestroy(c->s_aux[i]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
@@ -637,12 +637,12 @@ extern "C" int ss_render_dev(ss_ctx* c, const ss_source* items, int n_items, voi
     }
     // fork: chunks alternate between two internal streams / scratch buffers; join back into `stream`
     CK(cudaEventRecord(c->ev_fork, (cudaStream_t)stream));
-    CK(cudaStreamWaitEvent(c->s_aux[0], c->ev_fork, 0));
-    CK(cudaStreamWaitEvent(c->s_aux[1], c->ev_fork, 0));
+    for (int i = 0; i < ss_ctx::kAux; ++i) CK(cudaStreamWaitEvent(c->s_aux[i], c->ev_fork, 0));
+    c->ring_pos = 0;                                    // slot k % kRing <-> stream k % kAux
     int rc = SS_OK;
     for (size_t k = 0; k < n_chunks && rc == SS_OK; ++k)
-        rc = launch_chunk(c, items, cuts[k], cuts[k + 1], c->s_aux[k & 1], (int)(k & 1));
-    for (int i = 0; i < 2; ++i) {
+        rc = launch_chunk(c, items, cuts[k], cuts[k + 1], c->s_aux[k % ss_ctx::kAux], (int)(k % ss_ctx::kAux));
+    for (int i = 0; i < ss_ctx::kAux; ++i) {
         CK(cudaEventRecord(c->ev_join[i], c->s_aux[i]));
         CK(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_join[i], 0));
     }
