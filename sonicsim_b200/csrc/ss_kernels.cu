@@ -7,11 +7,16 @@
 // so only the two positions a sample needs are ever convolved (2/P of the reference's work) and the
 // (P, C, N) intermediate of :86 is never materialised.
 //
-// Three launches per chunk of sources:
-//   k_spectra : real rows (RIR partitions, dry windows) -> half spectra (two rows per complex FFT)
-//   k_render  : per (block, channel): Z = sum_part X[b-part] (H[p] + i H[p+1]); one 8192-point
-//               inverse FFT in shared memory gives both positions' convolutions as Re / Im; the
-//               closing radix-2 is fused with the per-sample lerp and the (C, N) store.
+// Launches per chunk of sources:
+//   k_blocks  : block table (waypoint-aligned or 4096-grid) + dense numbering of the work items; skipped
+//               when the trajectory bounds are on the host, which then builds the same tables itself
+//   k_prepare : real rows (RIR partitions, dry windows) -> half spectra (two rows per complex FFT);
+//               one warp per block fills that block's k_render work items
+//   k_render  : persistent CTAs; per transform Z = sum_part X[b-part] (H[p] + i H[p+1]) from spectra the
+//               bulk-copy engine staged in shared memory one transform ahead; one 8192-point inverse FFT
+//               gives both positions' convolutions as Re / Im; the closing radix-2 is fused with the
+//               per-sample lerp and the (C, N) store.  <LONG>: RIR partitions >= 1; <FAST>: all-aligned chunk.
+// Consecutive chunks rotate through three streams / scratch buffers so that they overlap.
 // fp32 throughout (the reference is float32 end to end), no cuFFT.
 #include <cuda_runtime.h>
 #include <math.h>
