@@ -216,12 +216,13 @@ def run_ours(args, rank, local_rank, world):
     h_srcs = [render.MovingSource(x.numpy(), h.numpy(), b) for x, h, b in h_items]
     h_outs_t = [torch.empty((C, N), dtype=torch.float32).pin_memory() for _ in range(n_src)]
     h_outs = [t.numpy() for t in h_outs_t]
+    plan = R.plan_host(h_srcs, h_outs)            # batch validated and bound to its pinned buffers once
     for _ in range(max(1, min(W, 2))):
-        R.render_host(h_srcs, h_outs)
+        plan.run()
     barrier()
     t_e0 = time.perf_counter()
     for _ in range(K):
-        R.render_host(h_srcs, h_outs)
+        plan.run()                                # one ss_render_host call: H2D -> render -> D2H
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t_e0
     barrier()
@@ -277,7 +278,7 @@ def run_ours(args, rank, local_rank, world):
                        "parallelism": "units sharded across %d rank(s), no data-path collective" % world},
             "clocks": sampler.summary([(t_w0, t_w1), (t_e0, t_e1)]),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_b), "d2h_bytes_per_step": int(out_b),
-                    "ms_per_step": 1e3 * e2e_max / K, "api": "sonicsim_b200.render.Renderer.render_host -> ss_render_host",
+                    "ms_per_step": 1e3 * e2e_max / K, "api": "sonicsim_b200.render.Renderer.plan_host(...).run() -> ss_render_host",
                     "bit_identical_to_device_arm": same, "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",

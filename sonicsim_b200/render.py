@@ -40,14 +40,12 @@ class Renderer:
         self.ctx = _lib.context(device)
 
     # ------------------------------------------------------------------ host buffers
-    def render_host(self, sources: T.Sequence[T.Union[MovingSource, StaticSource]],
-                    outs: T.Optional[T.Sequence[np.ndarray]] = None,
-                    lufs_targets: T.Optional[T.Sequence[T.Optional[float]]] = None, sr: float = 16000,
-                    loudness_out: T.Optional[list] = None) -> T.List[np.ndarray]:
-        """Render every source; returns a list of (C, N) float32 arrays (pinned `outs` may be passed).
-        `lufs_targets[i]` (or None) additionally normalises stem i to that integrated loudness on
-        the device before the copy out - SonicSim_audio.lufs_norm fused behind the render
-        (SonicSet.py:97-101).  `loudness_out`, if a list, receives (measured LUFS, linear gain) per source."""
+    def plan_host(self, sources: T.Sequence[T.Union[MovingSource, StaticSource]],
+                  outs: T.Optional[T.Sequence[np.ndarray]] = None,
+                  lufs_targets: T.Optional[T.Sequence[T.Optional[float]]] = None, sr: float = 16000) -> "HostPlan":
+        """Validate a batch once and bind it to its host buffers; `plan.run()` then renders it with a single
+        C-ABI call (a generation loop refills the same pinned buffers and calls run() again).
+        See render_host for the arguments."""
         from .SonicSim_audio import gating_plan
         n = len(sources)
         items = (SsSource * n)()
@@ -86,13 +84,21 @@ class Renderer:
                                      n_e=len(brk) - 1, n_blocks=len(blo), rate=float(sr), block_size=float(block),
                                      target_lufs=float(lufs_targets[i]), result=results_l[i].ctypes.data)
                 keep.append((brk, blo, bhi))
-        if post is None:
-            _lib.check(self.lib.ss_render_host(self.ctx, items, n))
-        else:
-            _lib.check(self.lib.ss_render_host_ex(self.ctx, items, n, post))
-            if loudness_out is not None:
-                loudness_out[:] = [tuple(r) for r in results_l]
-        return results
+        return HostPlan(self, items, post, n, results, results_l, keep)
+
+    def render_host(self, sources: T.Sequence[T.Union[MovingSource, StaticSource]],
+                    outs: T.Optional[T.Sequence[np.ndarray]] = None,
+                    lufs_targets: T.Optional[T.Sequence[T.Optional[float]]] = None, sr: float = 16000,
+                    loudness_out: T.Optional[list] = None) -> T.List[np.ndarray]:
+        """Render every source; returns a list of (C, N) float32 arrays (pinned `outs` may be passed).
+        `lufs_targets[i]` (or None) additionally normalises stem i to that integrated loudness on
+        the device before the copy out - SonicSim_audio.lufs_norm fused behind the render
+        (SonicSet.py:97-101).  `loudness_out`, if a list, receives (measured LUFS, linear gain) per source."""
+        plan = self.plan_host(sources, outs, lufs_targets, sr)
+        res = plan.run()
+        if loudness_out is not None and lufs_targets is not None:
+            loudness_out[:] = plan.loudness()
+        return res
 
     # ------------------------------------------------------------------ device tensors
     def render_device(self, sources, outs, stream: T.Optional[int] = None):
@@ -137,6 +143,27 @@ class Renderer:
 
     def set_chunk_bytes(self, nbytes: int):
         _lib.check(self.lib.ss_set_chunk_bytes(self.ctx, int(nbytes)))
+
+
+class HostPlan:
+    """A validated batch bound to its host input / output buffers (Renderer.plan_host)."""
+
+    def __init__(self, renderer, items, post, n, results, results_l, keep):
+        self.renderer, self.items, self.post, self.n = renderer, items, post, n
+        self.results, self.results_l, self._keep = results, results_l, keep
+
+    def run(self) -> T.List[np.ndarray]:
+        """H2D -> render [-> loudness] -> D2H of the whole batch; returns the (C, N) output arrays."""
+        lib, ctx = self.renderer.lib, self.renderer.ctx
+        if self.post is None:
+            _lib.check(lib.ss_render_host(ctx, self.items, self.n))
+        else:
+            _lib.check(lib.ss_render_host_ex(ctx, self.items, self.n, self.post))
+        return self.results
+
+    def loudness(self) -> T.List[T.Tuple[float, float]]:
+        """(measured LUFS, linear gain) per source of the last run (NaN where no target was given)."""
+        return [tuple(r) for r in self.results_l]
 
 
 _default: T.Optional[Renderer] = None
