@@ -198,6 +198,7 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(K):
         R.render_device(d_srcs, d_outs)
     e1.record()
+    t_issue = time.perf_counter() - t_w0          # host time to enqueue the K steps (launch-bound if ~ device time)
     barrier()
     t_w1 = time.perf_counter()
     launches = R.launch_count()
@@ -238,6 +239,7 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dev_max, e2e_max = float(tt[0]), float(tt[1])
     counters = shard.gather_counters(step_audio * K, dev_s, step_alg * K, device=dev)
+    issue_all = shard.gather_counters(t_issue, e2e_s, 0.0, device=dev)
     total_audio = float(counters[:, 0].sum())
     value = total_audio / dev_max
     e2e_value = total_audio / e2e_max
@@ -275,7 +277,10 @@ def run_ours(args, rank, local_rank, world):
                        "sources_per_gpu_per_step": n_src,
                        "l2": "inputs %.0f MB + outputs %.0f MB per step are larger than the 126 MB L2 (no flush needed)"
                              % (in_b / 1e6, out_b / 1e6),
-                       "parallelism": "units sharded across %d rank(s), no data-path collective" % world},
+                       "parallelism": "units sharded across %d rank(s), no data-path collective" % world,
+                       "per_rank_ms_per_step": [round(1e3 * float(t) / K, 4) for t in counters[:, 1]],
+                       "per_rank_host_issue_ms_per_step": [round(1e3 * float(t) / K, 4) for t in issue_all[:, 0]],
+                       "per_rank_e2e_ms_per_step": [round(1e3 * float(t) / K, 3) for t in issue_all[:, 1]]},
             "clocks": sampler.summary([(t_w0, t_w1), (t_e0, t_e1)]),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_b), "d2h_bytes_per_step": int(out_b),
                     "ms_per_step": 1e3 * e2e_max / K, "api": "sonicsim_b200.render.Renderer.plan_host(...).run() -> ss_render_host",
