@@ -162,6 +162,7 @@ def run_ours(args, rank, local_rank, world):
     from sonicsim_b200 import render, shard
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    numa_node = shard.bind_to_gpu_numa(local_rank) if world > 1 else None      # keep pinned buffers socket-local
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -278,6 +279,7 @@ def run_ours(args, rank, local_rank, world):
                        "l2": "inputs %.0f MB + outputs %.0f MB per step are larger than the 126 MB L2 (no flush needed)"
                              % (in_b / 1e6, out_b / 1e6),
                        "parallelism": "units sharded across %d rank(s), no data-path collective" % world,
+                       "numa_node_rank0": numa_node,
                        "per_rank_ms_per_step": [round(1e3 * float(t) / K, 4) for t in counters[:, 1]],
                        "per_rank_host_issue_ms_per_step": [round(1e3 * float(t) / K, 4) for t in issue_all[:, 0]],
                        "per_rank_e2e_ms_per_step": [round(1e3 * float(t) / K, 3) for t in issue_all[:, 1]]},

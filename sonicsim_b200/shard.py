@@ -57,3 +57,28 @@ def aggregate_throughput(counters: np.ndarray) -> T.Tuple[float, float]:
     total_audio = float(counters[:, 0].sum())
     t_max = float(counters[:, 1].max())
     return total_audio / t_max, float(counters[:, 2].sum()) / t_max
+
+
+def bind_to_gpu_numa(cuda_index: int) -> T.Optional[int]:
+    """Pin this process (and therefore its first-touch pinned host buffers) to the CPUs of the NUMA node
+    the GPU hangs off, so that the H2D / D2H copies of the host path do not cross sockets.  Best effort:
+    returns the node id or None when the topology cannot be read."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(cuda_index)
+        bdf = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:          # noqa: BLE001
+        return None
