@@ -220,3 +220,32 @@ def test_large_mixed_batch_multi_chunk_two_streams():
             assert so.rel_rms(one, ref) < TOL
     finally:
         R.set_chunk_bytes(96 << 20)
+
+
+def test_host_plan_rerun_with_refilled_buffers():
+    """Renderer.plan_host binds buffers once; run() picks up new buffer contents (and new trajectories) each time."""
+    from sonicsim_b200 import render
+    rng = np.random.default_rng(123)
+    N, C, L, P = 30000, 2, 900, 5
+    x = so.synth_dry(rng, N)
+    h = so.synth_rirs(rng, P, C, L)
+    np.random.seed(1)
+    bounds = render.trajectory_bounds(so.synth_path(rng, P), N)
+    xs, hs_ = so.synth_dry(rng, N), so.synth_rirs(rng, 1, C, L)[0]
+    R = render.default_renderer()
+    plan = R.plan_host([render.MovingSource(x, h, bounds), render.StaticSource(xs, hs_)], lufs_targets=[-20.0, None])
+    for it in range(3):
+        outs = plan.run()
+        idx = np.repeat(np.arange(P - 1), np.diff(bounds))
+        w = np.concatenate([np.linspace(0, 1, n, endpoint=False) for n in np.diff(bounds)]).astype(np.float32)
+        ref = so.lufs_norm(np.ascontiguousarray(so.convolve_moving_receiver(x, h, idx, w).T), 16000, -20.0)[0].T
+        assert so.rel_rms(outs[0], ref) < TOL
+        assert so.rel_rms(outs[1], so.convolve_fixed_receiver(xs[None], hs_)) < TOL
+        lufs, gain = plan.loudness()[0]
+        assert np.isfinite(lufs) and gain > 0
+        # refill the bound buffers in place: new dry signal, new RIRs, new trajectory
+        x[:] = so.synth_dry(rng, N)
+        h[:] = so.synth_rirs(rng, P, C, L)
+        np.random.seed(10 + it)
+        bounds[:] = render.trajectory_bounds(so.synth_path(rng, P), N)
+        xs[:] = so.synth_dry(rng, N)
