@@ -329,7 +329,10 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk-mb", type=int, default=0, help="override the library's L2-sized spectra budget")
+    ap.add_argument("--tiny", action="store_true", help="(tests only) shrink the workload to seconds of CPU time")
     args = ap.parse_args()
+    if args.tiny:
+        CFG.update(P=6, C=2, L=512, N=24000)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
