@@ -693,6 +693,8 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
             if (post[i].rate != post[0].rate && post[0].brk) return SS_ERR_INVALID;
         }
     }
+    // an earlier asynchronous ss_render_dev may still be using scratch buffer 0 on its internal streams
+    for (int i = 0; i < ss_ctx::kAux; ++i) CK(cudaStreamWaitEvent(c->s_cmp, c->ev_join[i], 0));
     std::vector<int> cuts;
     make_chunks(c, items, n_items, cuts, c->chunk_bytes_host);
     std::vector<ss_source> dev(n_items);
