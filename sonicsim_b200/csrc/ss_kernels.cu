@@ -638,6 +638,7 @@ extern "C" int ss_render_dev(ss_ctx* c, const ss_source* items, int n_items, voi
             int st = launch_chunk(c, items, cuts[k], cuts[k + 1], (cudaStream_t)stream, 0);
             if (st) return st;
         }
+        CK(cudaEventRecord(c->ev_join[0], (cudaStream_t)stream));      // scratch buffer 0 busy until here
         return SS_OK;
     }
     // fork: chunks alternate between two internal streams / scratch buffers; join back into `stream`
