@@ -3,8 +3,8 @@
 meaning, return types and exception types; the arithmetic runs in the CUDA library (C ABI in
 include/sonicsim_b200.h).  No CPU fallback.
 
-Out of scope here: dry-stream assembly (:231-340) and generate_rir_combination
-(:342-400), which wrap Habitat / dataset files.
+Dry-stream assembly (:152-340) is re-exported from sonicsim_b200.dry (host logic, same `random` stream as the
+reference).  Out of scope: generate_rir_combination (:342-400), which wraps Habitat.
 
 Loudness follows pyloudnorm 0.1.1 (the reference's pin, ss-2.0.yaml:201), restated from its
 published algorithm because the package is not vendored in the reference: "parity unpinned".
@@ -16,6 +16,8 @@ import math
 import numpy as np
 
 from . import _lib
+from .dry import (create_background_audio, create_long_audio, get_random_wav_path,      # noqa: F401  (:152-340, host logic)
+                  get_random_wav_path_from_json)
 
 
 # ------------------------------------------------------------------------------------ loudness
