@@ -146,14 +146,22 @@ typedef struct {
     double* scratch;          /* ss_mix_scratch_doubles() doubles                                        */
     int64_t E;
     int32_t S, M;
-    float snr;                /* dB (reference: U(10, 20))                                               */
-    int32_t reserved;
+    float snr;                /* dB (reference: U(10, 20); enhancement variant U(-10, 15))               */
+    int32_t noise_delay;      /* 0, or overlap_audio's shift D in elements applied to the summed noise:
+                                 n[e] = (s[e-D] + s[e+D]) + s[e]  (enhancement/.../movingdatamodule.py:34-48,240) */
 } ss_mix_item;
 
 int64_t ss_mix_scratch_doubles(void);
 int ss_mix_dev(ss_ctx* ctx, const ss_mix_item* items, int n_items, void* stream);      /* device pointers, async */
 int ss_mix_host(ss_ctx* ctx, const float* speakers, const float* noises, const float* sirs, float snr,
                 float* mix, float* speakers_out, int32_t S, int32_t M, int64_t E);      /* host pointers */
+int ss_mix_host_ex(ss_ctx* ctx, const float* speakers, const float* noises, const float* sirs, float snr,
+                   float* mix, float* speakers_out, int32_t S, int32_t M, int64_t E, int32_t noise_delay);
+
+/* overlap_audio (enhancement/look2hear/datas/movingdatamodule.py:34-48): y[r][n] = (x[r][n-D] + x[r][n+D]) + x[r][n],
+ * zeros outside [0, T); x != y. */
+int ss_overlap_dev(ss_ctx* ctx, const float* x, float* y, int32_t rows, int64_t T, int64_t delay, void* stream);
+int ss_overlap_host(ss_ctx* ctx, const float* x, float* y, int32_t rows, int64_t T, int64_t delay);
 
 /* Counters since ss_create / ss_reset_stats: kernels launched and device time is NOT measured
  * here (bench.py uses CUDA events); this is the launch count bench.py reports as gpu_launches. */

@@ -9,6 +9,7 @@ them need neither /root/reference nor this script.  TEST INFRASTRUCTURE.
 """
 import os
 import sys
+import types
 
 import numpy as np
 
@@ -142,5 +143,64 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def golden_mix_noisy():
+    """f1 (enhancement variant): overlap_audio (:34-48), find_overlap_region (:50-75) and the noisy-mixture block of
+    the enhancement dataloader (enhancement/look2hear/datas/movingdatamodule.py235-257), exec'd verbatim."""
+    import random
+    import textwrap
+    import torch
+    src = open("/root/reference/enhancement/look2hear/datas/movingdatamodule.py").read().splitlines()
+    assert src[28].startswith("def compute_mch_rms_dB") and src[33].startswith("def overlap_audio"), (src[28], src[33])
+    assert src[49].startswith("def find_overlap_region") and src[75].strip() == "", (src[49], src[75])
+    ns = {"torch": torch, "np": np, "random": random}
+    exec("\n".join(src[28:75]), ns)
+    assert src[234].strip().startswith("all_noise = torch.sum") and src[256].strip().startswith("mix_wav ="), (src[234], src[256])
+    body = textwrap.dedent("\n".join(src[234:257]))
+    cases = {}
+    for k, (seed, T, rows, sr, delay) in enumerate([(71, 4000, 1, 500, 6), (72, 1000, 2, 16000, 0.01), (73, 300, 1, 100, 6)]):
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal((rows, T)).astype(np.float32)
+        y = ns["overlap_audio"](torch.from_numpy(x.copy()), sr, delay=delay)
+        cases[f"ov_x{k}"], cases[f"ov_y{k}"] = x, y.numpy()
+        cases[f"ov_sr{k}"], cases[f"ov_delay{k}"] = np.int64(sr), np.float64(delay)
+    cases["n_ov"] = np.int64(3)
+    for k, (seed, kw) in enumerate([(81, {}), (82, dict(min_overlap=1, max_overlap=2)),
+                                    (83, dict(max_duration=0.5, sample_rate=1000))]):
+        rng = np.random.default_rng(seed)
+        data = {}
+        for s in range(3):
+            starts = np.sort(rng.integers(0, 9000, 4))
+            data[f"spk{s}"] = {"start_end_points": [[int(a), int(a) + int(rng.integers(100, 900))] for a in starts]}
+        data["noise"] = {"other": 1}
+        random.seed(seed)
+        lo, hi = ns["find_overlap_region"](data, **kw)
+        cases[f"fo_points{k}"] = np.array([data[f"spk{s}"]["start_end_points"] for s in range(3)], dtype=np.int64)
+        cases[f"fo_out{k}"] = np.array([lo, hi], dtype=np.int64)
+        cases[f"fo_seed{k}"] = np.int64(seed)
+        cases[f"fo_kw{k}"] = np.array(repr(kw))
+    cases["n_fo"] = np.int64(3)
+    for k, (seed, M, T, sr, kinds) in enumerate([(91, 2, 12000, 1000, ["music", "noise"]), (92, 1, 8000, 1000, ["noise"]),
+                                                 (93, 1, 4000, 16000, ["music"])]):
+        rng = np.random.default_rng(seed)
+        spk = (rng.standard_normal(T) * 0.1).astype(np.float32)
+        noi = (rng.standard_normal((M, T)) * (1e-5 if k == 2 else 0.05)).astype(np.float32)
+        torch.manual_seed(seed)
+        snr = torch.Tensor(1).uniform_(-10, 15).numpy()
+        torch.manual_seed(seed)
+        env = dict(ns)
+        env.update(self=types.SimpleNamespace(sample_rate=sr), speaker_wavs=torch.from_numpy(spk.copy()),
+                   noise_wav=torch.from_numpy(noi.copy()), noise_types=kinds)
+        exec(body, env)
+        cases[f"mn_spk{k}"], cases[f"mn_noise{k}"], cases[f"mn_snr{k}"], cases[f"mn_sr{k}"] = spk, noi, snr, np.int64(sr)
+        cases[f"mn_mix{k}"] = env["mix_wav"].numpy()
+    cases["n_mn"] = np.int64(3)
+    np.savez_compressed(os.path.join(OUT, "mix_noisy.npz"), **cases)
+    print("mix_noisy.npz", os.path.getsize(os.path.join(OUT, "mix_noisy.npz")))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "mix_noisy":
+        golden_mix_noisy()
+    else:
+        main()
+        golden_mix_noisy()

@@ -253,6 +253,50 @@ def mix_stems(speaker_wav, noise_wav, sirs, snr):
     return all_speech + all_noise, speaker_wav                                     # :124
 
 
+def overlap_audio(waveform, sample_rate, delay=6):
+    """enhancement/look2hear/datas/movingdatamodule.py:34-48: y[n] = (x[n-D] + x[n+D]) + x[n] with zeros outside
+    [0, T), D = int(delay * sample_rate); waveform (rows, T) float32 ndarray."""
+    x = np.asarray(waveform, dtype=np.float32)
+    T = x.shape[1]
+    D = int(delay * sample_rate)                                                   # :35
+    fwd = np.zeros_like(x)
+    bwd = np.zeros_like(x)
+    if D < T:
+        fwd[:, D:] = x[:, : T - D]                                                 # :38,42
+        bwd[:, : T - D] = x[:, D:]                                                 # :39,43
+    return (fwd + bwd) + x                                                         # :46
+
+
+def find_overlap_region(data, min_overlap=2, max_overlap=3, max_duration=None, sample_rate=None, rand=None):
+    """:50-75: rejection sampling of [start, end] (inclusive `random.randint` draws) until the number of utterance
+    boundaries inside it is in [min_overlap, max_overlap]; `max_duration` is (as in the reference) a MINIMUM."""
+    import random as _random
+    rand = rand or _random
+    pts = [p for src in data.values() if "start_end_points" in src for p in src["start_end_points"]]   # :51-54
+    lo = min(p[0] for p in pts)
+    hi = max(p[1] for p in pts)
+    while True:
+        a = rand.randint(lo, hi)                                                   # :61
+        b = rand.randint(a, hi)                                                    # :62
+        if max_duration is not None and sample_rate is not None and (b - a) / sample_rate < max_duration:
+            continue                                                               # :64-67
+        n = sum(a <= p[0] <= b or a <= p[1] <= b for p in pts)                     # :69-72
+        if min_overlap <= n <= max_overlap:
+            return a, b
+
+
+def mix_noisy(speaker_wavs, noise_wav, snr, sample_rate, delay=6):
+    """:235-257 (noisy single-speaker mixture of the enhancement dataloader): summed noise stems, overlap_audio over
+    the flattened signal, SNR gain (clamped at +40 dB) against the speaker stem, sum.  torch float32 in/out."""
+    import torch
+    all_noise = torch.sum(noise_wav, dim=0)                                        # :239
+    shape = all_noise.shape
+    all_noise = torch.from_numpy(overlap_audio(all_noise.reshape(1, -1).numpy(), sample_rate, delay)).reshape(shape)
+    gain = min(compute_mch_rms_dB(speaker_wavs) - compute_mch_rms_dB(all_noise) - snr, 40)    # :243-246
+    all_noise = all_noise * 10. ** (float(np.asarray(gain).reshape(-1)[0]) / 20.)              # :247
+    return speaker_wavs + all_noise                                                # :257
+
+
 # ------------------------------------------------------------------- synthetic inputs
 def synth_rirs(rng, P, C, L, sr=16000, t60=0.5):
     """decaying Gaussian noise, small random per-position delay, divided by the

@@ -35,7 +35,7 @@ class SsMixItem(ctypes.Structure):
     _fields_ = [("speakers", ctypes.c_void_p), ("noises", ctypes.c_void_p), ("sirs", ctypes.c_void_p),
                 ("mix", ctypes.c_void_p), ("speakers_out", ctypes.c_void_p), ("scratch", ctypes.c_void_p),
                 ("E", ctypes.c_int64), ("S", ctypes.c_int32), ("M", ctypes.c_int32), ("snr", ctypes.c_float),
-                ("reserved", ctypes.c_int32)]
+                ("noise_delay", ctypes.c_int32)]
 
 
 class SsPostLufs(ctypes.Structure):
@@ -119,6 +119,9 @@ def load():
         lib.ss_mix_scratch_doubles.restype = i64
         lib.ss_mix_dev.argtypes = [vp, ctypes.POINTER(SsMixItem), ctypes.c_int, vp]
         lib.ss_mix_host.argtypes = [vp, vp, vp, vp, ctypes.c_float, vp, vp, i32, i32, i64]
+        lib.ss_mix_host_ex.argtypes = [vp, vp, vp, vp, ctypes.c_float, vp, vp, i32, i32, i64, i32]
+        lib.ss_overlap_dev.argtypes = [vp, vp, vp, i32, i64, i64, vp]
+        lib.ss_overlap_host.argtypes = [vp, vp, vp, i32, i64, i64]
         lib.ss_launch_count.argtypes = [vp]
         lib.ss_launch_count.restype = i64
         lib.ss_reset_stats.argtypes = [vp]
@@ -135,7 +138,8 @@ def load():
 
 EXPORTS = ["ss_version", "ss_strerror", "ss_last_cuda_error", "ss_create", "ss_destroy",
            "ss_set_chunk_bytes", "ss_render_dev", "ss_render_host", "ss_render_host_ex", "ss_convolve_fixed_receiver",
-           "ss_convolve_moving_receiver", "ss_loudness_dev", "ss_lufs_norm_host", "ss_mix_scratch_doubles", "ss_mix_dev", "ss_mix_host", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
+           "ss_convolve_moving_receiver", "ss_loudness_dev", "ss_lufs_norm_host", "ss_mix_scratch_doubles", "ss_mix_dev", "ss_mix_host",
+           "ss_mix_host_ex", "ss_overlap_dev", "ss_overlap_host", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
            "ss_host_free"]
 
 

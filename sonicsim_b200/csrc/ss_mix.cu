@@ -23,7 +23,7 @@ struct MixItem {
     long long E;
     int S, M;
     float snr;
-    int pad_;
+    int delay;             // overlap_audio shift of the summed noise in elements (0 = none)
 };
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
@@ -38,6 +38,22 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     return r;          // valid in thread 0
 }
 
+
+// summed noise stems at element e; with delay D > 0 the enhancement dataloader's overlap_audio
+// (enhancement/look2hear/datas/movingdatamodule.py:34-48) on top: (s[e-D] + s[e+D]) + s[e], zeros outside [0, E)
+__device__ __forceinline__ float noise_sum(const MixItem& it, long long e) {
+    float n = 0.f;
+    for (int m = 0; m < it.M; ++m) n += it.noise[(long long)m * it.E + e];
+    return n;
+}
+__device__ __forceinline__ float noise_at(const MixItem& it, long long e) {
+    const float n = noise_sum(it, e);
+    if (it.delay <= 0) return n;
+    const float f = e >= it.delay ? noise_sum(it, e - it.delay) : 0.f;
+    const float b = e + it.delay < it.E ? noise_sum(it, e + it.delay) : 0.f;
+    return __fadd_rn(__fadd_rn(f, b), n);
+}
+
 // pass 1: sum of squares of every speaker stem and of the summed noise
 __global__ void __launch_bounds__(256) k_mix_energy(const MixItem* __restrict__ items) {
     __shared__ double sh[8];
@@ -48,8 +64,7 @@ __global__ void __launch_bounds__(256) k_mix_energy(const MixItem* __restrict__ 
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < it.E; e += (long long)gridDim.x * blockDim.x) {
 #pragma unroll
         for (int s = 0; s < kMaxStems; ++s) if (s < it.S) { float v = it.spk[(long long)s * it.E + e]; acc[s] += (double)(v * v); }
-        float n = 0.f;
-        for (int m = 0; m < it.M; ++m) n += it.noise[(long long)m * it.E + e];
+        const float n = noise_at(it, e);
         acc[kMaxStems] += (double)(n * n);
     }
 #pragma unroll
@@ -126,9 +141,7 @@ __global__ void __launch_bounds__(256) k_mix_write(const MixItem* __restrict__ i
             if (it.spk_out) it.spk_out[(long long)s * it.E + e] = v;
             sp += v;
         }
-        float n = 0.f;
-        for (int m = 0; m < it.M; ++m) n += it.noise[(long long)m * it.E + e];
-        it.mix[e] = sp + n * gn;
+        it.mix[e] = sp + noise_at(it, e) * gn;
     }
 }
 
@@ -144,6 +157,7 @@ extern "C" int ss_mix_dev(ss_ctx* c, const ss_mix_item* items, int n_items, void
         if (!a.speakers || !a.noises || !a.mix || !a.scratch || a.E <= 0 || a.S < 1 || a.M < 1) return SS_ERR_INVALID;
         if (a.S > kMaxStems || a.M > kMaxStems) return SS_ERR_UNSUPPORTED;
         if (a.S > 1 && !a.sirs) return SS_ERR_INVALID;
+        if (a.noise_delay < 0) return SS_ERR_INVALID;
     }
     const size_t bytes = align_up(sizeof(MixItem) * n_items, 16);
     int slot; char *hblk, *dblk;
@@ -153,7 +167,7 @@ extern "C" int ss_mix_dev(ss_ctx* c, const ss_mix_item* items, int n_items, void
         const ss_mix_item& a = items[i];
         MixItem m; memset(&m, 0, sizeof(m));
         m.spk = a.speakers; m.noise = a.noises; m.sirs = a.sirs; m.mix = a.mix; m.spk_out = a.speakers_out;
-        m.scratch = a.scratch; m.E = a.E; m.S = a.S; m.M = a.M; m.snr = a.snr;
+        m.scratch = a.scratch; m.E = a.E; m.S = a.S; m.M = a.M; m.snr = a.snr; m.delay = a.noise_delay;
         h[i] = m;
     }
     CK(cudaMemcpyAsync(c->d_desc[slot], c->h_desc[slot], bytes, cudaMemcpyHostToDevice, stream));
@@ -171,9 +185,9 @@ extern "C" int ss_mix_dev(ss_ctx* c, const ss_mix_item* items, int n_items, void
 
 extern "C" int64_t ss_mix_scratch_doubles(void) { return (int64_t)kMixBlocks * (kMaxStems + 2) + kMaxStems + 1; }
 
-extern "C" int ss_mix_host(ss_ctx* c, const float* speakers, const float* noises, const float* sirs, float snr,
-                           float* mix, float* speakers_out, int32_t S, int32_t M, int64_t E) {
-    if (!c || !speakers || !noises || !mix || S < 1 || M < 1 || E <= 0) return SS_ERR_INVALID;
+extern "C" int ss_mix_host_ex(ss_ctx* c, const float* speakers, const float* noises, const float* sirs, float snr,
+                              float* mix, float* speakers_out, int32_t S, int32_t M, int64_t E, int32_t noise_delay) {
+    if (!c || !speakers || !noises || !mix || S < 1 || M < 1 || E <= 0 || noise_delay < 0) return SS_ERR_INVALID;
     CK(cudaSetDevice(c->device));
     const size_t o_spk = 0, o_noise = align_up(4 * (size_t)S * E, 256), o_mix = o_noise + align_up(4 * (size_t)M * E, 256);
     const size_t o_sir = o_mix + align_up(4 * (size_t)E, 256), o_scr = o_sir + 256;
@@ -195,11 +209,66 @@ extern "C" int ss_mix_host(ss_ctx* c, const float* speakers, const float* noises
     ss_mix_item it; memset(&it, 0, sizeof(it));
     it.speakers = (const float*)(b + o_spk); it.noises = (const float*)(b + o_noise); it.sirs = (const float*)(b + o_sir);
     it.mix = (float*)(b + o_mix); it.speakers_out = speakers_out ? (float*)(b + o_spk) : nullptr;
-    it.scratch = (double*)(b + o_scr); it.E = E; it.S = S; it.M = M; it.snr = snr;
+    it.scratch = (double*)(b + o_scr); it.E = E; it.S = S; it.M = M; it.snr = snr; it.noise_delay = noise_delay;
     int rc = ss_mix_dev(c, &it, 1, (void*)st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(mix, b + o_mix, 4 * (size_t)E, cudaMemcpyDeviceToHost, st));
     if (speakers_out) CK(cudaMemcpyAsync(speakers_out, b + o_spk, 4 * (size_t)S * E, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SS_OK;
+}
+
+extern "C" int ss_mix_host(ss_ctx* c, const float* speakers, const float* noises, const float* sirs, float snr,
+                           float* mix, float* speakers_out, int32_t S, int32_t M, int64_t E) {
+    return ss_mix_host_ex(c, speakers, noises, sirs, snr, mix, speakers_out, S, M, E, 0);
+}
+
+// ---- overlap_audio (enhancement/look2hear/datas/movingdatamodule.py:34-48) as a stand-alone op
+namespace {
+__global__ void __launch_bounds__(256) k_overlap(const float* __restrict__ x, float* __restrict__ y, long long T, long long D) {
+    const float* xr = x + (long long)blockIdx.y * T;
+    float* yr = y + (long long)blockIdx.y * T;
+    for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < T; n += (long long)gridDim.x * blockDim.x) {
+        const float f = n >= D ? xr[n - D] : 0.f;
+        const float b = n + D < T ? xr[n + D] : 0.f;
+        yr[n] = __fadd_rn(__fadd_rn(f, b), xr[n]);
+    }
+}
+}  // namespace
+
+extern "C" int ss_overlap_dev(ss_ctx* c, const float* x, float* y, int32_t rows, int64_t T, int64_t delay, void* stream_) {
+    if (!c || !x || !y || x == y || rows < 0 || T < 0 || delay < 0) return SS_ERR_INVALID;
+    if (rows == 0 || T == 0) return SS_OK;
+    if (rows > 65535) return SS_ERR_UNSUPPORTED;
+    CK(cudaSetDevice(c->device));
+    long long nb = (T + 255) / 256;
+    if (nb > 1184) nb = 1184;                       // 8 waves of 148 SMs, grid-stride beyond that
+    k_overlap<<<dim3((unsigned)nb, (unsigned)rows), 256, 0, (cudaStream_t)stream_>>>(x, y, T, delay);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    return SS_OK;
+}
+
+extern "C" int ss_overlap_host(ss_ctx* c, const float* x, float* y, int32_t rows, int64_t T, int64_t delay) {
+    if (!c || !x || !y || rows < 0 || T < 0 || delay < 0) return SS_ERR_INVALID;
+    if (rows == 0 || T == 0) return SS_OK;
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = 4 * (size_t)rows * (size_t)T, o_y = align_up(bytes, 256), total = o_y + align_up(bytes, 256);
+    ss_ctx::Slot& sl = c->slot[0];
+    cudaStream_t st = c->s_cmp;
+    CK(cudaStreamSynchronize(st));
+    if (total > sl.in_cap) {
+        CK(cudaDeviceSynchronize());
+        if (sl.d_in) CK(cudaFree(sl.d_in));
+        sl.d_in = nullptr; sl.in_cap = 0;
+        CK(cudaMalloc((void**)&sl.d_in, align_up(total, 1 << 20)));
+        sl.in_cap = align_up(total, 1 << 20);
+    }
+    char* b = sl.d_in;
+    CK(cudaMemcpyAsync(b, x, bytes, cudaMemcpyHostToDevice, st));
+    int rc = ss_overlap_dev(c, (const float*)b, (float*)(b + o_y), rows, T, delay, (void*)st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(y, b + o_y, bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return SS_OK;
 }

@@ -45,3 +45,67 @@ def mix_stems(speaker_wav, noise_wav, sirs: T.Optional[T.Sequence[float]] = None
                                  float(np.asarray(snr).reshape(-1)[0]), mix.ctypes.data, spk_out.ctypes.data, S, M, E)
     _lib.check(st)
     return torch.from_numpy(mix), torch.from_numpy(spk_out)
+
+
+# ---- enhancement dataloader variant (enhancement/look2hear/datas/movingdatamodule.py) -------------------------
+def overlap_audio(waveform, sample_rate, delay=6):
+    """:34-48, same signature: waveform (rows, T) float32 tensor -> waveform + itself shifted by +-delay seconds
+    (zeros shifted in), summed in the reference's order.  Runs on the GPU (`ss_overlap_host`)."""
+    import torch
+    if waveform.dim() != 2:
+        raise IndexError("Dimension out of range (expected to be in range of [-2, 1], but got 1)")   # .size(1) at :42
+    x = np.ascontiguousarray(waveform.detach().cpu().numpy(), dtype=np.float32)
+    y = np.empty_like(x)
+    delay_samples = int(delay * sample_rate)                                                      # :35
+    if delay_samples < 0:
+        raise ValueError("negative delay")
+    _lib.check(_lib.load().ss_overlap_host(_lib.context(), x.ctypes.data, y.ctypes.data, x.shape[0], x.shape[1],
+                                           delay_samples))
+    return torch.from_numpy(y)
+
+
+def find_overlap_region(data, min_overlap=2, max_overlap=3, max_duration=None, sample_rate=None):
+    """:50-75, same signature and the same `random.randint` draws (host logic): a region [start, end] of the scene
+    holding between `min_overlap` and `max_overlap` utterance boundaries of json_data.json's `start_end_points`.
+    As in the reference, `max_duration` acts as a minimum length in seconds."""
+    import random
+    points = [pt for source in data.values() if "start_end_points" in source for pt in source["start_end_points"]]
+    if not points:
+        raise ValueError("min() arg is an empty sequence")                                       # :57
+    first = min(pt[0] for pt in points)
+    last = max(pt[1] for pt in points)
+    check_len = max_duration is not None and sample_rate is not None
+    while True:
+        start = random.randint(first, last)
+        end = random.randint(start, last)
+        if check_len and (end - start) / sample_rate < max_duration:
+            continue
+        inside = 0
+        for pt in points:
+            inside += (start <= pt[0] <= end) or (start <= pt[1] <= end)
+        if min_overlap <= inside <= max_overlap:
+            return start, end
+
+
+def mix_noisy(speaker_wavs, noise_wav, snr: T.Optional[float] = None, sample_rate=16000, delay=6):
+    """The noisy single-speaker mixture of the enhancement dataloader (:235-257): sum of the noise stems,
+    `overlap_audio(delay)` over the flattened sum, SNR gain against the speaker stem clamped at +40 dB, sum.
+    speaker_wavs (..., T), noise_wav (M, ..., T) float32 tensors -> mix_wav.  `snr=None` draws
+    `torch.Tensor(1).uniform_(-10, 15)` like :244 / :250.  One fused GPU pass set (`ss_mix_host_ex`)."""
+    import torch
+    if snr is None:
+        snr = torch.Tensor(1).uniform_(-10, 15).numpy()
+    spk = np.ascontiguousarray(speaker_wavs.detach().cpu().numpy(), dtype=np.float32)
+    noi = np.ascontiguousarray(noise_wav.detach().cpu().numpy(), dtype=np.float32)
+    if noi.ndim < 1 or spk.shape != noi.shape[1:]:
+        raise RuntimeError("The size of tensor a must match the size of tensor b")               # broadcast at :257
+    E = int(spk.size)
+    delay_samples = int(delay * sample_rate)
+    if delay_samples < 0:
+        raise ValueError("negative delay")
+    mix = np.empty(spk.shape, dtype=np.float32)
+    st = _lib.load().ss_mix_host_ex(_lib.context(), spk.ctypes.data, noi.ctypes.data, None,
+                                    float(np.asarray(snr).reshape(-1)[0]), mix.ctypes.data, None, 1, noi.shape[0], E,
+                                    min(delay_samples, 2**31 - 1))
+    _lib.check(st)
+    return torch.from_numpy(mix)

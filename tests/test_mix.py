@@ -14,6 +14,69 @@ def test_oracle_matches_reference_lines_bit_exact(golden):
         assert np.array_equal(mix.numpy(), g[f"mix{k}"]) and np.array_equal(spk.numpy(), g[f"spk_out{k}"])
 
 
+def _fo_data(g, k):
+    pts = g[f"fo_points{k}"]
+    data = {f"spk{s}": {"start_end_points": pts[s].tolist()} for s in range(pts.shape[0])}
+    data["noise"] = {"other": 1}
+    return data
+
+
+def test_oracle_enhancement_variant_bit_exact(golden):
+    """overlap_audio / find_overlap_region / the noisy-mixture block of the enhancement dataloader
+    (enhancement/look2hear/datas/movingdatamodule.py:34-75, 235-257)."""
+    import ast
+    import random
+    g = golden("mix_noisy")
+    for k in range(int(g["n_ov"])):
+        assert np.array_equal(so.overlap_audio(g[f"ov_x{k}"], int(g[f"ov_sr{k}"]), float(g[f"ov_delay{k}"])), g[f"ov_y{k}"])
+    for k in range(int(g["n_fo"])):
+        random.seed(int(g[f"fo_seed{k}"]))
+        assert so.find_overlap_region(_fo_data(g, k), **ast.literal_eval(str(g[f"fo_kw{k}"]))) == tuple(g[f"fo_out{k}"])
+    for k in range(int(g["n_mn"])):
+        m = so.mix_noisy(torch.from_numpy(g[f"mn_spk{k}"]), torch.from_numpy(g[f"mn_noise{k}"]), g[f"mn_snr{k}"], int(g[f"mn_sr{k}"]))
+        assert np.array_equal(m.numpy(), g[f"mn_mix{k}"])
+
+
+def test_find_overlap_region_dropin_same_random_stream(golden):
+    import ast
+    import random
+    from sonicsim_b200 import mix as smix
+    g = golden("mix_noisy")
+    for k in range(int(g["n_fo"])):
+        random.seed(int(g[f"fo_seed{k}"]))
+        assert smix.find_overlap_region(_fo_data(g, k), **ast.literal_eval(str(g[f"fo_kw{k}"]))) == tuple(g[f"fo_out{k}"])
+        after = random.random()
+        random.seed(int(g[f"fo_seed{k}"]))
+        so.find_overlap_region(_fo_data(g, k), **ast.literal_eval(str(g[f"fo_kw{k}"])))
+        assert random.random() == after                        # consumed exactly as many draws
+    with pytest.raises(ValueError):
+        smix.find_overlap_region({"noise": {}})
+
+
+@pytest.mark.gpu
+def test_gpu_enhancement_variant_matches_golden(golden):
+    from sonicsim_b200 import mix as smix
+    g = golden("mix_noisy")
+    for k in range(int(g["n_ov"])):
+        y = smix.overlap_audio(torch.from_numpy(g[f"ov_x{k}"]), int(g[f"ov_sr{k}"]), delay=float(g[f"ov_delay{k}"]))
+        assert np.array_equal(y.numpy(), g[f"ov_y{k}"])        # additions in the reference's order: bit-exact
+    for k in range(int(g["n_mn"])):
+        m = smix.mix_noisy(torch.from_numpy(g[f"mn_spk{k}"]), torch.from_numpy(g[f"mn_noise{k}"]), g[f"mn_snr{k}"],
+                           sample_rate=int(g[f"mn_sr{k}"]))
+        assert m.shape == torch.Size(g[f"mn_mix{k}"].shape)
+        assert so.rel_rms(m.numpy(), g[f"mn_mix{k}"]) < 1e-5
+    # seeded draw like :244
+    torch.manual_seed(3)
+    m1 = smix.mix_noisy(torch.from_numpy(g["mn_spk0"]), torch.from_numpy(g["mn_noise0"]), sample_rate=int(g["mn_sr0"]))
+    torch.manual_seed(3)
+    snr = torch.Tensor(1).uniform_(-10, 15).numpy()
+    m2 = so.mix_noisy(torch.from_numpy(g["mn_spk0"]), torch.from_numpy(g["mn_noise0"]), snr, int(g["mn_sr0"]))
+    assert so.rel_rms(m1.numpy(), m2.numpy()) < 1e-5
+    # delay longer than the clip: both shifted copies vanish
+    x = torch.from_numpy(g["ov_x2"])
+    assert np.array_equal(smix.overlap_audio(x, 16000, delay=6).numpy(), g["ov_x2"])
+
+
 @pytest.mark.gpu
 def test_gpu_mix_matches_golden(golden):
     from sonicsim_b200 import mix as smix
