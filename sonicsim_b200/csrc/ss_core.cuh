@@ -36,6 +36,20 @@ SS_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y
 SS_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 SS_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 SS_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// a + w b, a - w b (4 FMA each) and 2 t - s (2 FMA): a twiddled radix-2 butterfly (t + w b, t - w b) costs
+// 6 instructions as (s = cfma(t, w, b), twice_minus(t, s)) instead of 8 as (cmul, cadd, csub).
+#if defined(__CUDA_ARCH__)
+#define SS_FMA(a, b, c) __fmaf_rn(a, b, c)
+#else
+#define SS_FMA(a, b, c) ((a) * (b) + (c))
+#endif
+SS_HD float2 cfma(float2 a, float2 w, float2 b) {
+    return make_float2(SS_FMA(-w.y, b.y, SS_FMA(w.x, b.x, a.x)), SS_FMA(w.y, b.x, SS_FMA(w.x, b.y, a.y)));
+}
+SS_HD float2 cfms(float2 a, float2 w, float2 b) {
+    return make_float2(SS_FMA(w.y, b.y, SS_FMA(-w.x, b.x, a.x)), SS_FMA(-w.y, b.x, SS_FMA(-w.x, b.y, a.y)));
+}
+SS_HD float2 twice_minus(float2 t, float2 s) { return make_float2(SS_FMA(2.f, t.x, -s.x), SS_FMA(2.f, t.y, -s.y)); }
 // multiply by -i (forward) or +i (inverse)
 template <bool INV> SS_HD float2 rot90(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
 // conjugate the twiddle for the inverse transform
@@ -103,35 +117,58 @@ SS_HD void fft4(float2& v0, float2& v1, float2& v2, float2& v3) {
     v0 = cadd(a0, a2); v2 = csub(a0, a2); v1 = cadd(a1, a3); v3 = csub(a1, a3);
 }
 
+// radix-4 butterfly whose inputs 1..3 still have to be multiplied by w1..w3 (input 0 by w0 when TW0):
+// the products are folded into the first add/sub level.
+template <bool INV, bool TW0>
+SS_HD void fft4_tw(float2& v0, float2& v1, float2& v2, float2& v3, float2 w0, float2 w1, float2 w2, float2 w3) {
+    const float2 t0 = TW0 ? cmul(v0, w0) : v0;
+    const float2 a0 = cfma(t0, w2, v2), a1 = twice_minus(t0, a0);
+    const float2 t1 = cmul(v1, w1);
+    const float2 a2 = cfma(t1, w3, v3), a3 = rot90<INV>(twice_minus(t1, a2));
+    v0 = cadd(a0, a2); v2 = csub(a0, a2); v1 = cadd(a1, a3); v3 = csub(a1, a3);
+}
+
+// second level of fft16: v[4a + c] *= W16^(a c) folded into the radix-4 butterflies (forward W16 = exp(-2 pi i / 16))
+template <bool INV>
+SS_HD void fft16_level2(float2 (&v)[16]) {
+    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+    const float2 one = make_float2(1.f, 0.f);
+    fft4<INV>(v[0], v[1], v[2], v[3]);
+    fft4_tw<INV, false>(v[4], v[5], v[6], v[7], one, dirw<INV>(make_float2(C1, -S1)), dirw<INV>(make_float2(H, -H)),
+                        dirw<INV>(make_float2(S1, -C1)));                                   // a = 1: W^1, W^2, W^3
+    {                                                                                       // a = 2: W^2, W^4 = -+i, W^6
+        const float2 r2 = rot90<INV>(v[10]);
+        const float2 a0 = cadd(v[8], r2), a1 = csub(v[8], r2);
+        const float2 t1 = cmul(v[9], dirw<INV>(make_float2(H, -H)));
+        const float2 a2 = cfma(t1, dirw<INV>(make_float2(-H, -H)), v[11]), a3 = rot90<INV>(twice_minus(t1, a2));
+        v[8] = cadd(a0, a2); v[10] = csub(a0, a2); v[9] = cadd(a1, a3); v[11] = csub(a1, a3);
+    }
+    fft4_tw<INV, false>(v[12], v[13], v[14], v[15], one, dirw<INV>(make_float2(S1, -C1)), dirw<INV>(make_float2(-H, -H)),
+                        dirw<INV>(make_float2(-C1, S1)));                                   // a = 3: W^3, W^6, W^9
+}
+
 // In-register 16-point DFT (4 x 4).  Input natural order v[n]; output X[a + 4c] is left in
 // v[4a + c] (see out16()).
 template <bool INV>
 SS_HD void fft16(float2 (&v)[16]) {
-    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
 #pragma unroll
     for (int b = 0; b < 4; ++b) fft4<INV>(v[b], v[b + 4], v[b + 8], v[b + 12]);
-    // twiddle v[b + 4a] *= W16^(a b)   (forward W16 = exp(-2 pi i / 16))
-    v[5]  = cmul(v[5],  dirw<INV>(make_float2(C1, -S1)));      // ab = 1
-    v[6]  = cmul(v[6],  dirw<INV>(make_float2(H, -H)));        // ab = 2
-    v[7]  = cmul(v[7],  dirw<INV>(make_float2(S1, -C1)));      // ab = 3
-    v[9]  = cmul(v[9],  dirw<INV>(make_float2(H, -H)));        // ab = 2
-    v[10] = rot90<INV>(v[10]);                                 // ab = 4
-    v[11] = cmul(v[11], dirw<INV>(make_float2(-H, -H)));       // ab = 6
-    v[13] = cmul(v[13], dirw<INV>(make_float2(S1, -C1)));      // ab = 3
-    v[14] = cmul(v[14], dirw<INV>(make_float2(-H, -H)));       // ab = 6
-    v[15] = cmul(v[15], dirw<INV>(make_float2(-C1, S1)));      // ab = 9
+    fft16_level2<INV>(v);
+}
+// the same with the inter-pass twiddles v[r] *= tab[r * STRIDE], r = 1..15, folded into the first level
+template <bool INV, int STRIDE>
+SS_HD void fft16_tw(float2 (&v)[16], const float2* tab) {
+    float2 w[16];
+    w[0] = make_float2(1.f, 0.f);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) fft4<INV>(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3]);
+    for (int r = 1; r < 16; ++r) w[r] = dirw<INV>(ldg_cached(tab + r * STRIDE));
+    fft4_tw<INV, false>(v[0], v[4], v[8], v[12], w[0], w[4], w[8], w[12]);
+#pragma unroll
+    for (int b = 1; b < 4; ++b) fft4_tw<INV, true>(v[b], v[b + 4], v[b + 8], v[b + 12], w[b], w[b + 4], w[b + 8], w[b + 12]);
+    fft16_level2<INV>(v);
 }
 // register slot that holds output index r after fft16
 SS_HD constexpr int out16(int r) { return 4 * (r & 3) + (r >> 2); }
-
-// v[r] *= tab[r * stride], r = 1..15 (tab points at the entry of this butterfly's k)
-template <bool INV, int STRIDE>
-SS_HD void twiddle16(float2 (&v)[16], const float2* tab) {
-#pragma unroll
-    for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], dirw<INV>(ldg_cached(tab + r * STRIDE)));
-}
 
 // ---------------------------------------------------------------------------------------
 // Stockham passes on a padded shared-memory array `s` (float2[kPadF]).
@@ -158,8 +195,7 @@ SS_HD void pass_load(const float2* s, int j, float2 (&v)[16]) {
 // Pass B (Ns = 16): twiddle exp(-+2 pi i k r / 256), k = j % 16
 template <bool INV>
 SS_HD void passB_compute(int j, float2 (&v)[16], const Tables& T) {
-    twiddle16<INV, 16>(v, T.twB + (j & 15));
-    fft16<INV>(v);
+    fft16_tw<INV, 16>(v, T.twB + (j & 15));
 }
 // destination (j / 16) * 256 + (j % 16) + 16 r, padded = (j / 16) * 272 + (j % 16) + 17 r
 SS_HD void passB_store(float2* s, int j, const float2 (&v)[16]) {
@@ -173,28 +209,25 @@ SS_HD void passB_store(float2* s, int j, const float2 (&v)[16]) {
 // butterfly j + 256 the same points of the second one.
 template <bool INV>
 SS_HD void passC_compute(int j, float2 (&v)[16], const Tables& T) {
-    twiddle16<INV, 256>(v, T.twC + (j & 255));
-    fft16<INV>(v);
+    fft16_tw<INV, 256>(v, T.twC + (j & 255));
 }
 
 // Closing radix-2 (Ns = 4096) for thread t: lo/hi are the pass-C results of butterflies t and t+256.
 // Returns through lo[slot] the points t + 256 r and through hi[slot] the points 4096 + t + 256 r,
 // slot = out16(r).
+// u[r] = exp(-+2 pi i (t + 256 r) / 8192) = wt * exp(-+2 pi i r / 32), r < 16 (wt = tw[t], already
+// direction-adjusted): seven products, the upper eight are quarter-turn rotations of the lower eight.
 template <bool INV>
-SS_HD float2 final_twiddle(int t, int r, float2 wt /* tw[t], already direction-adjusted */) {
-    // exp(-+2 pi i (t + 256 r) / 8192) = wt * exp(-+2 pi i r / 32)
-    const float c32[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
-                           0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f,
-                           0.19509032201612825f, 0.f, -0.19509032201612825f, -0.38268343236508977f,
-                           -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
-                           -0.92387953251128674f, -0.98078528040323043f};
-    const float s32[16] = {0.f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f,
-                           0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f,
-                           0.98078528040323043f, 1.f, 0.98078528040323043f, 0.92387953251128674f,
-                           0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
-                           0.38268343236508977f, 0.19509032201612825f};
-    float2 c = make_float2(c32[r], INV ? s32[r] : -s32[r]);
-    return cmul(wt, c);
+SS_HD void final_twiddles(float2 wt, float2 (&u)[16]) {
+    const float c32[8] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                          0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f};
+    const float s32[8] = {0.f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f,
+                          0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f};
+    u[0] = wt;
+#pragma unroll
+    for (int r = 1; r < 8; ++r) u[r] = cmul(wt, make_float2(c32[r], INV ? s32[r] : -s32[r]));
+#pragma unroll
+    for (int r = 0; r < 8; ++r) u[r + 8] = rot90<INV>(u[r]);
 }
 
 // ---------------------------------------------------------------------------------------

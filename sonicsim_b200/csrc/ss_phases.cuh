@@ -222,14 +222,14 @@ SS_HD void passB2(int t, float2* s, Regs32& R, const Tables& T) {
 SS_HD void spectra_phase3_compute(int t, Regs32& R, const Tables& T) {
     passC_compute<false>(t, R.a, T);
     passC_compute<false>(t + 256, R.b, T);
-    float2 wt = ldg_cached(T.tw + t);
+    float2 u[16];
+    final_twiddles<false>(ldg_cached(T.tw + t), u);
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         const int sl = out16(r);
-        float2 tmp = cmul(R.b[sl], final_twiddle<false>(t, r, wt));
-        float2 lo = R.a[sl];
-        R.a[sl] = cadd(lo, tmp);
-        R.b[sl] = csub(lo, tmp);
+        const float2 lo = R.a[sl], hi = cfma(lo, u[r], R.b[sl]);
+        R.a[sl] = hi;
+        R.b[sl] = twice_minus(lo, hi);
     }
 }
 // natural order to shared: pad(t + 256 r) = pad(t) + 272 r, pad(4096 + i) = 4352 + pad(i)
@@ -371,11 +371,12 @@ SS_HD void render_phase1(int t, float2* s, Regs32& R) {
 SS_HD void render_phase3(int t, Regs32& R, const Tables& T) {
     passC_compute<true>(t, R.a, T);
     passC_compute<true>(t + 256, R.b, T);
-    float2 wt = dirw<true>(ldg_cached(T.tw + t));
+    float2 u[16];
+    final_twiddles<true>(dirw<true>(ldg_cached(T.tw + t)), u);
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         const int sl = out16(r);
-        R.a[sl] = csub(R.a[sl], cmul(R.b[sl], final_twiddle<true>(t, r, wt)));
+        R.a[sl] = cfms(R.a[sl], u[r], R.b[sl]);
     }
 }
 // hat functions of positions (p, p+1) at a sample that lies in segment sg with weight w:
