@@ -198,7 +198,7 @@ constexpr int kRenderSmem = kPadF * (int)sizeof(float2) + kSpecBytes;         //
 // source under aligned blocking (one transform per block, two positions each, one segment per block).
 template <bool LONG, bool FAST>
 __global__ void __launch_bounds__(kThreads, SS_RENDER_MINB)
-k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr) {
+k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr, int n_items_host) {
     extern __shared__ __align__(128) float2 smem[];
     __shared__ __align__(16) RItem s_item[2];
     __shared__ __align__(16) XDesc s_desc[2];
@@ -209,7 +209,8 @@ k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr) {
     float2* const sHq = smem + kPadF;
     const Tables T{g_tw, g_twB, g_twC};
     const int t = threadIdx.x;
-    const int n_items = *n_items_ptr;          // written by k_blocks (aligned blocking: known only on the device)
+    // table length: known on the host when it built the tables, otherwise written by k_blocks
+    const int n_items = n_items_host >= 0 ? n_items_host : *n_items_ptr;
 
     // thread-0 iterator state
     int it_cur = blockIdx.x;          // item of the transform most recently published
@@ -584,9 +585,10 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
     const int grid_r = pr < c->sm_count * SS_RENDER_MINB ? pr : c->sm_count * SS_RENDER_MINB;
     bool any_long = false, all_aligned = true;
     for (int i = 0; i < n; ++i) { any_long = any_long || hs[i].K > 1; all_aligned = all_aligned && hs[i].aligned; }
-    if (any_long) k_render<true, false><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total);
-    else if (all_aligned && !getenv("SS_NO_FAST")) k_render<false, true><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total);
-    else k_render<false, false><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total);
+    const int n_known = host_tables ? total_items : -1;
+    if (any_long) k_render<true, false><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total, n_known);
+    else if (all_aligned && !getenv("SS_NO_FAST")) k_render<false, true><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total, n_known);
+    else k_render<false, false><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total, n_known);
     CK(cudaGetLastError());
     if (c->profiling) { CK(cudaEventRecord(pf.e2, stream)); c->prof.push_back(pf); }
     c->launches += 2;

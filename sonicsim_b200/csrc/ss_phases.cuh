@@ -413,16 +413,19 @@ SS_HD void render_epilogue(int t, const XDesc& d, const Regs32& R) {
     } else if (FAST || (mode == MODE_MOVING_BOUNDS && d.p_lo + 1 == d.p_hi)) {
         // the block lies inside one segment (always so under aligned blocking): sg = p for every
         // sample, 16 independent weight computations, lerp = (1 - w) Re z + w Im z
-        const int b0 = d.bounds[p];
+        // The 16 weights first, unguarded (no memory access), so that their int -> double -> float chains
+        // interleave; (double)(n - b0) = d0 + 256 r exactly.
+        const double d0 = (double)(nbase - d.bounds[p]);
         const double step = d.rstep[p];
+        float w[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) w[r] = (float)((d0 + 256.0 * r) * step);   // == np.linspace(0, 1, num, False)[i] as float32
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const int n = nbase + 256 * r;
-            if (n < n_end) {
-                const float w = (float)((double)(n - b0) * step);   // == np.linspace(0, 1, num, False)[i] as float32
-                const float2 z = R.a[out16(r)];
-                row[n] = lerp_terms(one_minus(w), z.x, w, z.y);
-            }
+            const float2 z = R.a[out16(r)];
+            const float v = lerp_terms(one_minus(w[r]), z.x, w[r], z.y);
+            if (n < n_end) row[n] = v;
         }
     } else if (mode == MODE_MOVING_BOUNDS) {
         const int* const bounds = d.bounds;
