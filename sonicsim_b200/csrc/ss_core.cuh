@@ -109,6 +109,9 @@ SS_HD float one_minus(float w) {
 //   twC[r * 256 + k] = exp(-2 pi i k r / 4096)          r < 16, k < 256 (pass C)
 // r-major so that a warp (consecutive k) reads consecutive words.
 struct Tables { const float2* tw; const float2* twB; const float2* twC; };
+#ifndef SS_TWC_STREAM_FROM
+#define SS_TWC_STREAM_FROM 16      // rows >= this of the pass-C table bypass L1 (experiment knob)
+#endif
 constexpr int kTabB = 16 * 16, kTabC = 16 * 256;
 
 template <bool INV>
@@ -161,7 +164,8 @@ SS_HD void fft16_tw(float2 (&v)[16], const float2* tab) {
     float2 w[16];
     w[0] = make_float2(1.f, 0.f);
 #pragma unroll
-    for (int r = 1; r < 16; ++r) w[r] = dirw<INV>(ldg_cached(tab + r * STRIDE));
+    for (int r = 1; r < 16; ++r)
+        w[r] = dirw<INV>((STRIDE == 256 && r >= SS_TWC_STREAM_FROM) ? ldg_stream(tab + r * STRIDE) : ldg_cached(tab + r * STRIDE));
     fft4_tw<INV, false>(v[0], v[4], v[8], v[12], w[0], w[4], w[8], w[12]);
 #pragma unroll
     for (int b = 1; b < 4; ++b) fft4_tw<INV, true>(v[b], v[b + 4], v[b + 8], v[b + 12], w[b], w[b + 4], w[b + 8], w[b + 12]);
