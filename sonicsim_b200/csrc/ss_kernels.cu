@@ -96,14 +96,29 @@ k_blocks(const Source* __restrict__ srcs, int n_src, int* __restrict__ total_ite
 //   [nh, nh + nx)      two dry windows         -> two half spectra
 //   [nh + nx, ...)     8 blocks each (one warp per block): position range of the block and its
 //                      k_render work items (RItem)
+// A CTA lives ~9 us, so the chain of dependent loads in front of its first row load matters: for chunks of up
+// to kPrepInline sources the source table and its prefix sums travel as kernel parameters (constant bank)
+// instead of global memory (binary search + descriptor = 4-5 L2 round trips per CTA).
+constexpr int kPrepInline = 24;
+struct PrepParams {
+    int n_inline;                      // 0: use the global tables
+    int prefix[kPrepInline + 1];
+    Source srcs[kPrepInline];
+};
+static_assert(sizeof(PrepParams) <= 4000, "kernel parameter space");
+
+template <bool INL>
 __global__ void __launch_bounds__(kThreads, 2)
-k_prepare(const Source* __restrict__ srcs, const int* __restrict__ prefix, int n_src, RItem* __restrict__ items) {
+k_prepare(const Source* __restrict__ srcs_g, const int* __restrict__ prefix_g, int n_src, RItem* __restrict__ items,
+          const __grid_constant__ PrepParams pp) {
     extern __shared__ float2 smem[];
     const Tables T{g_tw, g_twB, g_twC};
     const int t = threadIdx.x;
-    const int si = find_source(prefix, n_src, blockIdx.x);
-    const Source& S = srcs[si];
-    int local = blockIdx.x - prefix[si];
+    int si = 0;
+    if (INL) { for (int i = 1; i < kPrepInline; ++i) si += (i < n_src && pp.prefix[i] <= (int)blockIdx.x) ? 1 : 0; }
+    else si = find_source(prefix_g, n_src, blockIdx.x);
+    const Source& S = INL ? pp.srcs[si] : srcs_g[si];
+    int local = blockIdx.x - (INL ? pp.prefix[si] : prefix_g[si]);
     Row ra, rb;
     const int nh = spectra_pairs_h(S), nx = spectra_pairs_x(S);
     if (local >= nh + nx) {
@@ -332,7 +347,8 @@ extern "C" int ss_create(int device, ss_ctx** out) {
     }
     CK(cudaMemcpyToSymbol(g_twB, tb.data(), sizeof(float2) * kTabB));
     CK(cudaMemcpyToSymbol(g_twC, tc.data(), sizeof(float2) * kTabC));
-    CK(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
+    CK(cudaFuncSetAttribute(k_prepare<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
+    CK(cudaFuncSetAttribute(k_prepare<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
     CK(cudaFuncSetAttribute(k_render<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
     CK(cudaFuncSetAttribute(k_render<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
     CK(cudaFuncSetAttribute(k_render<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
@@ -579,7 +595,16 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
         CK(cudaGetLastError());
         c->launches += 1;
     }
-    k_prepare<<<ps, kThreads, kPadF * (int)sizeof(float2), stream>>>(ds, dps, n, d_items);
+    {
+        static thread_local PrepParams pp;             // 3.2 KB: not on the stack
+        pp.n_inline = n <= kPrepInline ? n : 0;
+        if (pp.n_inline) {
+            memcpy(pp.prefix, hps, sizeof(int) * (size_t)(n + 1));
+            memcpy(pp.srcs, hs, sizeof(Source) * (size_t)n);
+        }
+        if (pp.n_inline) k_prepare<true><<<ps, kThreads, kPadF * (int)sizeof(float2), stream>>>(ds, dps, n, d_items, pp);
+        else k_prepare<false><<<ps, kThreads, kPadF * (int)sizeof(float2), stream>>>(ds, dps, n, d_items, pp);
+    }
     CK(cudaGetLastError());
     if (c->profiling) CK(cudaEventRecord(pf.e1, stream));
     const int grid_r = pr < c->sm_count * SS_RENDER_MINB ? pr : c->sm_count * SS_RENDER_MINB;
