@@ -297,7 +297,8 @@ def run_ours(args, rank, local_rank, world):
                          "path_frac": achieved_path / peak, "launch_pairs_timed": int(n_pairs),
                          "timing": "kernel_ms / k_prepare_ms: CUDA events recorded by the library on the launching stream "
                                    "around every launch, K steps repeated right after the timed region with the chunk overlap "
-                                   "(two internal streams) switched off so that each kernel runs alone; path_achieved: "
+                                   "(three internal streams) switched off so that each kernel runs alone; per launch position "
+                                   "the median over the K steps is used; path_achieved: "
                                    "algorithmic bytes of the timed region / its device time (overlap on)"},
         }
         if world == 1 and not args.no_cpu_baseline:

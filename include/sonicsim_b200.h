@@ -171,7 +171,9 @@ void ss_reset_stats(ss_ctx* ctx);
 /* Per-kernel device timing with CUDA events recorded on the launching stream around k_spectra and
  * k_render (bench.py's roofline numbers).  ss_get_profile waits for the recorded launches, returns
  * the summed milliseconds of each kernel and the number of (k_spectra, k_render) launch pairs since
- * the previous call, and clears the record. */
+ * the previous call, and clears the record.  While profiling is on, chunks run one after the other on the
+ * caller's stream behind a 0.3 ms idle kernel (so no interval contains a wait for the host), and the sums
+ * are built from the median over calls of each launch position (repeat the same call to use this). */
 int ss_set_profiling(ss_ctx* ctx, int on);
 int ss_get_profile(ss_ctx* ctx, double* ms_spectra, double* ms_render, int64_t* n_pairs);
 

@@ -37,7 +37,8 @@ struct ss_ctx {
     bool single_stream = false;   // experiment knob (SS_SINGLE_STREAM=1): no chunk overlap
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profiling = false;
-    struct Prof { cudaEvent_t e0, e1, e2; };
+    struct Prof { cudaEvent_t e0, e1, e2; int chunk; };   // chunk = position of the launch pair inside its render call
+    int prof_chunk = 0;
     std::vector<Prof> prof;
 };
 

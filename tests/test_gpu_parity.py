@@ -222,6 +222,32 @@ def test_large_mixed_batch_multi_chunk_two_streams():
         R.set_chunk_bytes(96 << 20)
 
 
+def test_many_small_sources_in_one_chunk():
+    """More sources in one chunk than k_prepare takes as kernel parameters (24): the global-table variant of the
+    kernel == the same sources rendered one by one (parameter variant)."""
+    from sonicsim_b200 import render
+    rng = np.random.default_rng(7)
+    R = render.default_renderer()
+    srcs, dev, outs = [], [], []
+    for i in range(41):
+        N, C, P, L = int(rng.integers(2000, 9000)), int(rng.integers(1, 4)), int(rng.integers(2, 6)), int(rng.integers(8, 700))
+        x, h = so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L)
+        np.random.seed(100 + i)
+        b = render.trajectory_bounds(so.synth_path(rng, P), N)
+        srcs.append((x, h, b))
+        dev.append(render.MovingSource(torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda(), torch.from_numpy(b).cuda(), b))
+        outs.append(torch.empty((C, N), device="cuda"))
+    R.render_device(dev, outs)
+    torch.cuda.synchronize()
+    for (x, h, b), o in zip(srcs, outs):
+        one = R.render_host([render.MovingSource(x, h, b)])[0]
+        assert np.array_equal(o.cpu().numpy(), one)
+    x, h, b = srcs[0]
+    idx = np.repeat(np.arange(len(b) - 1), np.diff(b))
+    w = np.concatenate([np.linspace(0, 1, n, endpoint=False) for n in np.diff(b)]).astype(np.float32)
+    assert so.rel_rms(outs[0].cpu().numpy(), so.convolve_moving_receiver(x, h, idx, w)) < TOL
+
+
 def test_host_plan_rerun_with_refilled_buffers():
     """Renderer.plan_host binds buffers once; run() picks up new buffer contents (and new trajectories) each time."""
     from sonicsim_b200 import render
