@@ -219,6 +219,9 @@ constexpr int kRenderSmem = kPadF * (int)sizeof(float2) + kSpecBytes;         //
 // once pass C of transform k has read it out — so form_z never waits on L2.
 // LONG: RIR partitions >= 1 are accumulated (L > 4096).  FAST: every item of the chunk is a compact-trajectory
 // source under aligned blocking (one transform per block, two positions each, one segment per block).
+#ifndef SS_LONG_STAGED
+#define SS_LONG_STAGED 1          // 0: partitions >= 1 read with plain loads (form_z_parts), for comparison
+#endif
 template <bool LONG, bool FAST>
 __global__ void __launch_bounds__(kThreads, SS_RENDER_MINB)
 k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr, int n_items_host) {
@@ -264,12 +267,38 @@ k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr, i
     __syncthreads();
 
     Regs32 R;
+    unsigned ph = 0;                                  // parity of the staging barriers' current phase
     for (int k = 0;; ++k) {
-        mbar_wait(&s_bar[0], k & 1);
-        mbar_wait(&s_bar[1], k & 1);
+        mbar_wait(&s_bar[0], ph);
+        mbar_wait(&s_bar[1], ph);
+        ph ^= 1;
         const XDesc& d = s_desc[k & 1];
         if (!d.valid) break;
-        form_z<LONG, FAST>(t, sX, sHp, (FAST || d.Hq) ? sHq : nullptr, d, R);
+        if (LONG && SS_LONG_STAGED) {
+            // partitions 1 .. kparts-1 follow partition 0 through the same staging buffers
+            const float2* const q = d.Hq ? sHq : nullptr;
+            DcNy e;
+            long_stage<true>(t, sX, sHp, q, R, e);
+            const int kparts = d.kparts;
+            for (int part = 1; part < kparts; ++part) {
+                __syncthreads();                      // partition part-1 consumed by every thread
+                if (t == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
+                    bulk_g2s(sX, d.X - (size_t)part * kSpec, kSpecBytes, &s_bar[0]);
+                    bulk_g2s(sHp, d.Hp + (size_t)part * kSpec, kSpecBytes, &s_bar[0]);
+                    if (d.Hq) { mbar_expect_tx(&s_bar[1], kSpecBytes); bulk_g2s(sHq, d.Hq + (size_t)part * kSpec, kSpecBytes, &s_bar[1]); }
+                    else mbar_arrive(&s_bar[1]);
+                }
+                mbar_wait(&s_bar[0], ph);
+                mbar_wait(&s_bar[1], ph);
+                ph ^= 1;
+                long_stage<false>(t, sX, sHp, q, R, e);
+            }
+            long_finish(t, R, e);
+        } else {
+            form_z<LONG, FAST>(t, sX, sHp, (FAST || d.Hq) ? sHq : nullptr, d, R);
+        }
         __syncthreads();                              // staged spectra consumed, s_desc[k & 1] read by all
         if (t == 0) {
             // publish transform k+1 and start staging its Hq

@@ -361,6 +361,70 @@ SS_HD void form_z(int t, const float2* sX, const float2* sHp, const float2* sHq,
         R.a[0] = make_float2(pdc, qdc);
     }
 }
+// ---- long RIRs (LONG): the partitions of a transform pass through the staging buffers one after the other.
+// Stage j holds partition j of the two filters and the dry window 4096 j samples earlier (grid blocking);
+// stage 0 initialises the product slots (P_A, P_B, Q_A, Q_B) of form_z, later stages accumulate, long_finish
+// forms Z.  Thread 0 carries the packed (DC, Nyquist) products of all stages in `e`.
+struct DcNy { float pdc, pny, qdc, qny; };
+template <bool FIRST>
+SS_HD void long_stage(int t, const float2* sX, const float2* sHp, const float2* sHq, Regs32& R, DcNy& e) {
+    const int jB = passA_jB(t);
+    const float2 *xa_p = sX + t, *xb_p = sX + jB, *ha_p = sHp + t, *hb_p = sHp + jB;
+    if (sHq) {
+        const float2 *ga_p = sHq + t, *gb_p = sHq + jB;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const float2 xa = xa_p[512 * m], xb = xb_p[512 * m];
+            if (FIRST) {
+                R.a[m] = cmul(xa, ha_p[512 * m]);       R.b[m] = cmul(xb, hb_p[512 * m]);
+                R.b[15 - m] = cmul(xa, ga_p[512 * m]);  R.a[15 - m] = cmul(xb, gb_p[512 * m]);
+            } else {
+                cmac(R.a[m], xa, ha_p[512 * m]);        cmac(R.b[m], xb, hb_p[512 * m]);
+                cmac(R.b[15 - m], xa, ga_p[512 * m]);   cmac(R.a[15 - m], xb, gb_p[512 * m]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const float2 xa = xa_p[512 * m], xb = xb_p[512 * m];
+            if (FIRST) {
+                R.a[m] = cmul(xa, ha_p[512 * m]);       R.b[m] = cmul(xb, hb_p[512 * m]);
+                R.b[15 - m] = make_float2(0.f, 0.f);    R.a[15 - m] = make_float2(0.f, 0.f);
+            } else {
+                cmac(R.a[m], xa, ha_p[512 * m]);        cmac(R.b[m], xb, hb_p[512 * m]);
+            }
+        }
+    }
+    if (t == 0) {
+        const float2 x0 = sX[0], h0 = sHp[0];
+        if (FIRST) { e.pdc = x0.x * h0.x; e.pny = x0.y * h0.y; e.qdc = 0.f; e.qny = 0.f; }
+        else { e.pdc += x0.x * h0.x; e.pny += x0.y * h0.y; }
+        if (sHq) {
+            const float2 g0 = sHq[0];
+            if (FIRST) { e.qdc = x0.x * g0.x; e.qny = x0.y * g0.y; }
+            else { e.qdc += x0.x * g0.x; e.qny += x0.y * g0.y; }
+        }
+    }
+}
+SS_HD void long_finish(int t, Regs32& R, const DcNy& e) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        float2 PA = R.a[m], QA = R.b[15 - m], PB = R.b[m], QB = R.a[15 - m];
+        R.a[m] = z_direct(PA, QA);  R.b[15 - m] = z_mirror(PA, QA);
+        R.b[m] = z_direct(PB, QB);  R.a[15 - m] = z_mirror(PB, QB);
+    }
+    if (t == 0) {               // as in form_z: thread 0 owns butterflies 0 and 256 and the packed (DC, Nyquist) word
+        float2 tmp[8];
+#pragma unroll
+        for (int r = 8; r < 16; ++r) tmp[r - 8] = R.a[r];
+#pragma unroll
+        for (int r = 9; r < 16; ++r) R.a[r] = R.b[r - 1];
+#pragma unroll
+        for (int r = 8; r < 16; ++r) R.b[r] = tmp[r - 8];
+        R.a[8] = make_float2(e.pny, e.qny);
+        R.a[0] = make_float2(e.pdc, e.qdc);
+    }
+}
 SS_HD void render_phase1(int t, float2* s, Regs32& R) {
     fft16<true>(R.a); passA_store(s, passA_jA(t), R.a);
     fft16<true>(R.b); passA_store(s, passA_jB(t), R.b);

@@ -99,9 +99,10 @@ static void prepare_ranges(const Source& S, RItem* items) {
 
 // One persistent k_render CTA (`cta` of `grid`): same control flow as the kernel; the bulk copies
 // are done at the point where thread 0 issues them, the mbarrier waits are no-ops.
-static void cta_render(const RItem* items, int n_items, int cta, int grid, const Tables& T, bool fast) {
+static void cta_render(const RItem* items, int n_items, int cta, int grid, const Tables& T, bool fast, bool staged_long) {
     std::vector<float2> smem(kPadF + kSpec);
     std::vector<Regs32> R(kThreads);
+    std::vector<DcNy> E(kThreads);
     float2* const fftbuf = smem.data();
     float2* const sX = fftbuf;
     float2* const sHp = fftbuf + kSpec;
@@ -127,9 +128,22 @@ static void cta_render(const RItem* items, int n_items, int cta, int grid, const
     for (int k = 0;; ++k) {
         const XDesc& d = s_desc[k & 1];
         if (!d.valid) break;
-        for (int t = 0; t < kThreads; ++t) {
-            if (fast) form_z<false, true>(t, sX, sHp, sHq, d, R[t]);          // k_render<false, true>
-            else form_z<true, false>(t, sX, sHp, d.Hq ? sHq : nullptr, d, R[t]);   // k_render<true, false> covers <false, false> too
+        if (fast) {
+            for (int t = 0; t < kThreads; ++t) form_z<false, true>(t, sX, sHp, sHq, d, R[t]);          // k_render<false, true>
+        } else if (d.kparts <= 1 && !staged_long) {
+            for (int t = 0; t < kThreads; ++t) form_z<false, false>(t, sX, sHp, d.Hq ? sHq : nullptr, d, R[t]);
+        } else if (!staged_long) {
+            for (int t = 0; t < kThreads; ++t) form_z<true, false>(t, sX, sHp, d.Hq ? sHq : nullptr, d, R[t]);
+        } else {                                                                                      // k_render<true, false>
+            const float2* q = d.Hq ? sHq : nullptr;
+            for (int t = 0; t < kThreads; ++t) long_stage<true>(t, sX, sHp, q, R[t], E[t]);
+            for (int part = 1; part < d.kparts; ++part) {
+                memcpy(sX, d.X - (size_t)part * kSpec, sizeof(float2) * kSpec);                      // thread 0's bulk copies
+                memcpy(sHp, d.Hp + (size_t)part * kSpec, sizeof(float2) * kSpec);
+                if (d.Hq) memcpy(sHq, d.Hq + (size_t)part * kSpec, sizeof(float2) * kSpec);
+                for (int t = 0; t < kThreads; ++t) long_stage<false>(t, sX, sHp, q, R[t], E[t]);
+            }
+            for (int t = 0; t < kThreads; ++t) long_finish(t, R[t], E[t]);
         }
         {   // thread 0: publish transform k+1, stage its Hq
             XDesc nx; memset(&nx, 0, sizeof(nx));
@@ -184,7 +198,7 @@ int emu_render(const float* x, const float* rir, float* out, const int32_t* boun
     prepare_ranges(S, items.data());
     const int nr = counts[0] * items_per_block(S);
     const int grid = nr < 3 ? nr : 3;              // a few persistent CTAs, each looping over many items
-    for (int cta = 0; cta < grid; ++cta) cta_render(items.data(), nr, cta, grid, T, S.aligned != 0);
+    for (int cta = 0; cta < grid; ++cta) cta_render(items.data(), nr, cta, grid, T, S.aligned != 0, S.K > 1);
     return 0;
 }
 
