@@ -15,7 +15,8 @@
 //   k_render  : persistent CTAs; per transform Z = sum_part X[b-part] (H[p] + i H[p+1]) from spectra the
 //               bulk-copy engine staged in shared memory one transform ahead; one 8192-point inverse FFT
 //               gives both positions' convolutions as Re / Im; the closing radix-2 is fused with the
-//               per-sample lerp and the (C, N) store.  <LONG>: RIR partitions >= 1; <FAST>: all-aligned chunk.
+//               per-sample lerp and the (C, N) store.  <LONG>: RIR partitions >= 1 (staged one after the other);
+//               <FAST>: all-aligned chunk.
 // Consecutive chunks rotate through three streams / scratch buffers so that they overlap.
 // fp32 throughout (the reference is float32 end to end), no cuFFT.
 #include <cuda_runtime.h>
