@@ -189,15 +189,16 @@ def run_ours(args, rank, local_rank, world):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    dplan = R.plan_device(d_srcs, d_outs)           # batch bound to its device tensors once; run() = one C-ABI call
     for _ in range(W):
-        R.render_device(d_srcs, d_outs)
+        dplan.run()
     barrier()
     R.reset_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_w0 = time.perf_counter()
     e0.record()
     for _ in range(K):
-        R.render_device(d_srcs, d_outs)
+        dplan.run()
     e1.record()
     t_issue = time.perf_counter() - t_w0          # host time to enqueue the K steps (launch-bound if ~ device time)
     barrier()
@@ -208,7 +209,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- per-kernel timing (same K steps again, CUDA events around every launch)
     R.set_profiling(True)
     for _ in range(K):
-        R.render_device(d_srcs, d_outs)
+        dplan.run()
     torch.cuda.synchronize()
     ms_spec, ms_rend, n_pairs = R.get_profile()
     R.set_profiling(False)

@@ -104,10 +104,14 @@ class Renderer:
     def render_device(self, sources, outs, stream: T.Optional[int] = None):
         """`sources`: MovingSource / StaticSource whose fields are CUDA float32 / int32 tensors;
         `outs`: preallocated CUDA (C, N) tensors.  Asynchronous on `stream` (torch current stream)."""
-        import torch
+        self.plan_device(sources, outs).run(stream)
+
+    def plan_device(self, sources, outs) -> "DevicePlan":
+        """Bind a batch of device-resident sources to its output tensors once; `plan.run()` then renders it with a
+        single C-ABI call (a generation loop overwrites the same tensors and calls run() again)."""
         n = len(sources)
         items = (SsSource * n)()
-        keep = []
+        keep = [sources, outs]
         for i, s in enumerate(sources):
             if isinstance(s, StaticSource):
                 C, L = s.rir.shape
@@ -122,9 +126,7 @@ class Renderer:
                 items[i] = SsSource(x=s.dry.data_ptr(), rir=s.rirs.data_ptr(), out=outs[i].data_ptr(),
                                     bounds=s.bounds.data_ptr(), N=s.dry.numel(), P=P, C=C, L=L,
                                     mode=_lib.SS_MOVING_BOUNDS, bounds_host=bh.ctypes.data if bh is not None else None)
-        if stream is None:
-            stream = torch.cuda.current_stream().cuda_stream
-        _lib.check(self.lib.ss_render_dev(self.ctx, items, n, ctypes.c_void_p(stream)))
+        return DevicePlan(self, items, n, keep)
 
     def launch_count(self) -> int:
         return int(self.lib.ss_launch_count(self.ctx))
@@ -143,6 +145,20 @@ class Renderer:
 
     def set_chunk_bytes(self, nbytes: int):
         _lib.check(self.lib.ss_set_chunk_bytes(self.ctx, int(nbytes)))
+
+
+class DevicePlan:
+    """A batch of device-resident sources bound to its output tensors (Renderer.plan_device)."""
+
+    def __init__(self, renderer, items, n, keep):
+        self.renderer, self.items, self.n, self._keep = renderer, items, n, keep
+
+    def run(self, stream: T.Optional[int] = None):
+        """Asynchronous on `stream` (default: torch's current stream)."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.renderer.lib.ss_render_dev(self.renderer.ctx, self.items, self.n, ctypes.c_void_p(stream)))
 
 
 class HostPlan:

@@ -237,11 +237,17 @@ def test_many_small_sources_in_one_chunk():
         srcs.append((x, h, b))
         dev.append(render.MovingSource(torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda(), torch.from_numpy(b).cuda(), b))
         outs.append(torch.empty((C, N), device="cuda"))
-    R.render_device(dev, outs)
+    plan = R.plan_device(dev, outs)                  # bound once, run twice (second run after the outputs were cleared)
+    plan.run()
     torch.cuda.synchronize()
-    for (x, h, b), o in zip(srcs, outs):
+    first = [o.clone() for o in outs]
+    for o in outs:
+        o.zero_()
+    plan.run()
+    torch.cuda.synchronize()
+    for (x, h, b), o, f in zip(srcs, outs, first):
         one = R.render_host([render.MovingSource(x, h, b)])[0]
-        assert np.array_equal(o.cpu().numpy(), one)
+        assert np.array_equal(o.cpu().numpy(), one) and torch.equal(o, f)
     x, h, b = srcs[0]
     idx = np.repeat(np.arange(len(b) - 1), np.diff(b))
     w = np.concatenate([np.linspace(0, 1, n, endpoint=False) for n in np.diff(b)]).astype(np.float32)
