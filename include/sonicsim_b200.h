@@ -13,7 +13,9 @@
  *   - `*_host` entry points take HOST pointers (pinned memory gives full PCIe rate), copy in,
  *     render and copy out; they return after the results are in host memory.
  *   - an ss_ctx is NOT thread-safe: use one context per host thread (one process per GPU is the
- *     intended deployment); calls on one context are serialised by the caller.
+ *     intended deployment); calls on one context are serialised by the caller.  The context's scratch and
+ *     descriptor buffers are ordered against earlier work only through the stream a call is given: give
+ *     all `*_dev` calls of one context the same stream, or synchronise between calls that use different ones.
  *   - every function returns 0 (SS_OK) or a negative ss_status; ss_strerror() describes it.  The
  *     Python shim turns these into the exception types the reference raises (IndexError /
  *     ValueError), see INTEGRATION.md.

@@ -26,15 +26,16 @@ struct ss_ctx {
     char* h_desc[kRing] = {};
     char* d_desc[kRing] = {};
     size_t desc_cap[kRing] = {};
-    cudaEvent_t desc_ev[kRing];
+    cudaEvent_t desc_ev[kRing] = {};
     int ring_pos = 0;
     // host path
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
     struct Slot { char* d_in = nullptr; size_t in_cap = 0; char* d_out = nullptr; size_t out_cap = 0;
-                  cudaEvent_t ev_in, ev_done, ev_free; } slot[4];
+                  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_free = nullptr; } slot[4];
     static const int kSlots = 4;   // H2D may run up to 3 chunks ahead of the D2H that frees a slot
     int64_t launches = 0;
     bool single_stream = false;   // experiment knob (SS_SINGLE_STREAM=1): no chunk overlap
+    bool no_fast = false;         // experiment knob (SS_NO_FAST=1): never pick the all-aligned kernel variant
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Prof { cudaEvent_t e0, e1, e2; int chunk; };   // chunk = position of the launch pair inside its render call

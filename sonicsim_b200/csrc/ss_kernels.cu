@@ -25,6 +25,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <new>
 #include <vector>
 
 #include "ss_internal.h"
@@ -358,10 +359,10 @@ extern "C" const char* ss_strerror(int st) {
 }
 
 
-extern "C" int ss_create(int device, ss_ctx** out) {
-    if (!out) return SS_ERR_INVALID;
+extern "C" void ss_destroy(ss_ctx* c);
+
+static int init_ctx(ss_ctx* c, int device) {
     CK(cudaSetDevice(device));
-    ss_ctx* c = new ss_ctx();
     c->device = device;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -405,7 +406,18 @@ extern "C" int ss_create(int device, ss_ctx** out) {
         CK(cudaEventCreateWithFlags(&c->slot[i].ev_free, cudaEventDisableTiming));
     }
     c->single_stream = getenv("SS_SINGLE_STREAM") != nullptr;
+    c->no_fast = getenv("SS_NO_FAST") != nullptr;
     if (getenv("SS_HOST_CHUNK_MB")) c->chunk_bytes_host = (int64_t)atoi(getenv("SS_HOST_CHUNK_MB")) << 20;
+    return SS_OK;
+}
+
+extern "C" int ss_create(int device, ss_ctx** out) {
+    if (!out) return SS_ERR_INVALID;
+    *out = nullptr;
+    ss_ctx* c = new (std::nothrow) ss_ctx();
+    if (!c) return SS_ERR_NOMEM;
+    const int st = init_ctx(c, device);
+    if (st != SS_OK) { ss_destroy(c); return st; }        // releases whatever was created before the failure
     *out = c;
     return SS_OK;
 }
@@ -423,12 +435,14 @@ extern "C" void ss_destroy(ss_ctx* c) {
     for (int i = 0; i < ss_ctx::kRing; ++i) {
         if (c->h_desc[i]) cudaFreeHost(c->h_desc[i]);
         if (c->d_desc[i]) cudaFree(c->d_desc[i]);
-        cudaEventDestroy(c->desc_ev[i]);
+        if (c->desc_ev[i]) cudaEventDestroy(c->desc_ev[i]);
     }
     for (int i = 0; i < ss_ctx::kSlots; ++i) {
         if (c->slot[i].d_in) cudaFree(c->slot[i].d_in);
         if (c->slot[i].d_out) cudaFree(c->slot[i].d_out);
-        cudaEventDestroy(c->slot[i].ev_in); cudaEventDestroy(c->slot[i].ev_done); cudaEventDestroy(c->slot[i].ev_free);
+        if (c->slot[i].ev_in) cudaEventDestroy(c->slot[i].ev_in);
+        if (c->slot[i].ev_done) cudaEventDestroy(c->slot[i].ev_done);
+        if (c->slot[i].ev_free) cudaEventDestroy(c->slot[i].ev_free);
     }
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
@@ -667,7 +681,7 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
     for (int i = 0; i < n; ++i) { any_long = any_long || hs[i].K > 1; all_aligned = all_aligned && hs[i].aligned; }
     const int n_known = host_tables ? total_items : -1;
     if (any_long) k_render<true, false><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total, n_known);
-    else if (all_aligned && !getenv("SS_NO_FAST")) k_render<false, true><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total, n_known);
+    else if (all_aligned && !c->no_fast) k_render<false, true><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total, n_known);
     else k_render<false, false><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total, n_known);
     CK(cudaGetLastError());
     if (c->profiling) { CK(cudaEventRecord(pf.e2, stream)); c->prof.push_back(pf); }
@@ -790,6 +804,9 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
     std::vector<ss_source> dev(n_items);
     std::vector<ss_loud_item> loud;
     std::vector<double*> res_dev(n_items, nullptr);
+    // the pipeline proper; any failure falls through to the stream synchronisation below, so that no copy is
+    // still reading or writing the caller's buffers when this function returns
+    auto pipeline = [&]() -> int {
     int rc = SS_OK;
     for (size_t k = 0; k + 1 < cuts.size() && rc == SS_OK; ++k) {
         const int first = cuts[k], last = cuts[k + 1];
@@ -869,6 +886,9 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
         // the next chunk's H2D into the *other* slot may start now; it must not overtake the
         // render still reading this slot, which the per-slot ev_free wait above guarantees.
     }
+    return rc;
+    };
+    const int rc = pipeline();
     cudaError_t e1 = cudaStreamSynchronize(c->s_in), e2 = cudaStreamSynchronize(c->s_cmp), e3 = cudaStreamSynchronize(c->s_out);
     if (rc != SS_OK) return rc;
     CK(e1); CK(e2); CK(e3);
