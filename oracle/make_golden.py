@@ -198,9 +198,48 @@ def golden_mix_noisy():
     print("mix_noisy.npz", os.path.getsize(os.path.join(OUT, "mix_noisy.npz")))
 
 
+def golden_dry():
+    """f2: dry-stream assembly - the unmodified create_long_audio / create_background_audio
+    (SonicSim_audio.py:231-340) on the synthetic directory of oracle/dry_fixture.py, torchaudio.load stubbed."""
+    import json
+    import random
+    import tempfile
+    import pathlib
+    import torchaudio
+    from oracle import dry_fixture
+    _, ref = ref_loader.load(want_audio=True)
+    cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        spk, noise_json, load = dry_fixture.build(pathlib.Path(tmp))
+        ref.torchaudio = types.SimpleNamespace(transforms=torchaudio.transforms, load=load)
+        real_walk = os.walk
+        os.walk = dry_fixture.sorted_walk(real_walk)
+        try:
+            ref.print("")      # rich's first print draws from `random`
+            for seed in range(6):
+                random.seed(seed)
+                a, se, names = ref.create_long_audio(spk, 60)
+                random.seed(100 + seed)
+                b, bse, bnames = ref.create_background_audio(noise_json, 60)
+                cases.append({"seed": seed, "speech_sha256": dry_fixture.digest(a), "speech_shape": list(a.shape),
+                              "speech_spans": [list(map(int, x)) for x in se],
+                              "speech_names": [os.path.basename(n) for n in names],
+                              "bg_sha256": dry_fixture.digest(b), "bg_shape": list(b.shape),
+                              "bg_spans": [list(map(int, x)) for x in bse],
+                              "bg_names": [os.path.basename(n) for n in bnames]})
+        finally:
+            os.walk = real_walk
+    with open(os.path.join(OUT, "dry_assembly.json"), "w") as f:
+        json.dump({"cases": cases}, f, indent=1)
+    print("dry_assembly.json", len(cases), "cases")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mix_noisy":
         golden_mix_noisy()
+    elif len(sys.argv) > 1 and sys.argv[1] == "dry":
+        golden_dry()
     else:
         main()
         golden_mix_noisy()
+        golden_dry()

@@ -43,6 +43,11 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session")
 def emu():
     """CPU emulation of the CUDA kernels (tests/emu/ss_emu.cu), built with g++."""
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))

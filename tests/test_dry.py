@@ -1,6 +1,6 @@
-"""Dry-stream assembly (SonicSim_audio.py:152-340) against the live reference functions, with file loading
-stubbed on both sides (no audio files ship with the reference).  Runs where /root/reference exists."""
-import hashlib
+"""Dry-stream assembly (SonicSim_audio.py:152-340) against a golden record of the unmodified reference and, where
+/root/reference exists, against the live reference functions; file loading is stubbed on both sides (no audio
+files ship with the reference)."""
 import json
 import os
 import random
@@ -13,59 +13,51 @@ from oracle import ref_loader
 from sonicsim_b200 import dry
 
 
-def fake_loader(lengths, stereo=()):
-    def load(path):
-        n = lengths[os.path.basename(path)]
-        seed = int(hashlib.md5(os.path.basename(path).encode()).hexdigest()[:8], 16)
-        g = torch.Generator().manual_seed(seed)
-        ch = 2 if os.path.basename(path) in stereo else 1
-        return torch.randn((ch, n), generator=g) * 0.1, 16000
-    return load
+from oracle import dry_fixture
+from oracle.dry_fixture import fake_loader
+
+
+def test_dry_assembly_matches_reference_golden(tmp_path, monkeypatch, golden_dir):
+    """tests/golden/dry_assembly.json holds what the unmodified reference produced on this synthetic directory
+    (oracle/make_golden.py dry): file choice, placement and samples must be identical, seed by seed."""
+    g = json.load(open(os.path.join(golden_dir, "dry_assembly.json")))["cases"]
+    spk, noise_json, load = dry_fixture.build(tmp_path)
+    monkeypatch.setattr(os, "walk", dry_fixture.sorted_walk(os.walk))
+    for c in g:
+        random.seed(c["seed"])
+        a, se, names = dry.create_long_audio(spk, 60, loader=load)
+        assert [os.path.basename(n) for n in names] == c["speech_names"]
+        assert [list(map(int, x)) for x in se] == c["speech_spans"]
+        assert list(a.shape) == c["speech_shape"] and dry_fixture.digest(a) == c["speech_sha256"]
+        random.seed(100 + c["seed"])
+        b, bse, bnames = dry.create_background_audio(noise_json, 60, loader=load)
+        assert [os.path.basename(n) for n in bnames] == c["bg_names"]
+        assert [list(map(int, x)) for x in bse] == c["bg_spans"]
+        assert list(b.shape) == c["bg_shape"] and dry_fixture.digest(b) == c["bg_sha256"]
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
 def test_dry_assembly_matches_live_reference(tmp_path, monkeypatch):
     _, ref = ref_loader.load(want_audio=True)
-    rng = np.random.default_rng(0)
-    # a LibriSpeech-like speaker directory: utterances of 2-15 s plus a transcript file
-    spk = tmp_path / "spk" / "chapter"
-    spk.mkdir(parents=True)
-    lengths = {}
-    for i in range(14):
-        name = "61-%04d.flac" % i
-        (spk / name).write_bytes(b"")
-        lengths[name] = int(rng.integers(32000, 240000))
-    (spk / "61.trans.txt").write_text("x")
-    # noise / music length JSON
-    bg = {}
-    for i in range(6):
-        name = str(tmp_path / ("noise_%d.wav" % i))
-        bg[name] = int(rng.integers(100000, 700000))
-        lengths[os.path.basename(name)] = bg[name]
-    (tmp_path / "noise.json").write_text(json.dumps(bg))
-    load = fake_loader(lengths, stereo=("noise_1.wav", "noise_4.wav"))
+    spk, noise_json, load = dry_fixture.build(tmp_path)
 
     import types
     import torchaudio
     ref.torchaudio = types.SimpleNamespace(transforms=torchaudio.transforms, load=load)
-
-    # directory order is filesystem business (a fresh directory can even be listed differently the first time):
-    # give both implementations the same sorted listing
-    real_walk = os.walk
-    monkeypatch.setattr(os, "walk", lambda top, *a, **k: [(r, sorted(d), sorted(f)) for r, d, f in real_walk(top, *a, **k)])
+    monkeypatch.setattr(os, "walk", dry_fixture.sorted_walk(os.walk))
     ref.print("")          # the reference prints through rich, whose first use draws from `random`: get that out of the way
     for seed in range(6):
         random.seed(seed)
-        a_ref, se_ref, names_ref = ref.create_long_audio(str(tmp_path / "spk"), 60)
+        a_ref, se_ref, names_ref = ref.create_long_audio(spk, 60)
         random.seed(seed)
-        a, se, names = dry.create_long_audio(str(tmp_path / "spk"), 60, loader=load)
+        a, se, names = dry.create_long_audio(spk, 60, loader=load)
         assert names == names_ref and [tuple(x) for x in se] == [tuple(x) for x in se_ref]
         assert torch.equal(a, a_ref) and a.shape == (1, 960000)
 
         random.seed(100 + seed)
-        b_ref, bse_ref, bnames_ref = ref.create_background_audio(str(tmp_path / "noise.json"), 60)
+        b_ref, bse_ref, bnames_ref = ref.create_background_audio(noise_json, 60)
         random.seed(100 + seed)
-        b, bse, bnames = dry.create_background_audio(str(tmp_path / "noise.json"), 60, loader=load)
+        b, bse, bnames = dry.create_background_audio(noise_json, 60, loader=load)
         assert bnames == bnames_ref and [tuple(x) for x in bse] == [tuple(x) for x in bse_ref]
         assert torch.equal(b, b_ref)
 

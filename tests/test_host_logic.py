@@ -63,3 +63,33 @@ def test_index_error_like_reference():
     h = np.zeros((3, 1, 4), np.float32)
     with pytest.raises(IndexError):
         sm.convolve_moving_receiver(x, h, np.full(10, 2), np.zeros(10, np.float32))   # idx + 1 == P
+
+
+def test_ctypes_structs_match_the_c_header_layout(tmp_path):
+    """The ctypes mirrors in _lib.py against include/sonicsim_b200.h as gcc lays it out: same size and the same
+    offset for every field (the header is the contract a maintainer binds against)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from sonicsim_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"ss_source": _lib.SsSource, "ss_loud_item": _lib.SsLoudItem, "ss_post_lufs": _lib.SsPostLufs,
+             "ss_mix_item": _lib.SsMixItem}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sonicsim_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe)], check=True)     # the header is plain C
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
