@@ -508,6 +508,9 @@ extern "C" void ss_host_free(void* p) { if (p) cudaFreeHost(p); }
 static int validate_item(const ss_source& it) {
     if (!it.x || !it.rir || !it.out) return SS_ERR_INVALID;
     if (it.N <= 0 || it.C <= 0 || it.L <= 0 || it.P <= 0) return SS_ERR_INVALID;
+    // 32-bit sample / table indices inside the kernels: leave one FFT of headroom below 2^31
+    if (it.N > 0x7fffffff - 2 * kF) return SS_ERR_UNSUPPORTED;
+    if ((int64_t)it.P * it.C * ((it.L + kB - 1) / kB) > (int64_t)1 << 28) return SS_ERR_UNSUPPORTED;
     if (it.mode == SS_STATIC) { if (it.P != 1) return SS_ERR_INVALID; }
     else if (it.mode == SS_MOVING_BOUNDS) { if (it.P < 2 || !it.bounds) return SS_ERR_INVALID; }
     else if (it.mode == SS_MOVING_INDEXED) { if (it.P < 2 || !it.idx || !it.w) return SS_ERR_INVALID; }
