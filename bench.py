@@ -269,6 +269,21 @@ def run_ours(args, rank, local_rank, world):
                             "(%s; cold L2 per replay), scaled to this launch size" % tj["tag"])
         except Exception:
             pass
+        # instruction-issue view of the same launch (the kernel's actual limiter): warp instructions of one launch
+        # from the ncu capture, scaled to this launch size, over the issue slots of its measured duration
+        clocks = sampler.summary([(t_w0, t_w1), (t_e0, t_e1)])
+        issue = None
+        try:
+            sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+            mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 0.0)
+            winst = tj["k_render"]["warp_instructions"] / tj["sources_per_launch"] * (n_src * K / max(n_pairs, 1))
+            slots = k_render_s * sm_count * 4 * mhz * 1e6            # 4 schedulers per SM, one warp instruction per cycle each
+            if slots > 0:
+                issue = {"warp_instructions_per_launch": winst, "issue_slots": slots, "frac": winst / slots,
+                         "note": "warp instructions (ncu, %s) / (kernel_ms x %d SMs x 4 schedulers x %.0f MHz)"
+                                 % (tj["tag"], sm_count, mhz)}
+        except Exception:
+            pass
         in_b = sum(x.nbytes + h.nbytes + b.nbytes for x, h, b in items)
         out_b = n_src * C * N * 4
         line = {
@@ -284,7 +299,7 @@ def run_ours(args, rank, local_rank, world):
                        "per_rank_ms_per_step": [round(1e3 * float(t) / K, 4) for t in counters[:, 1]],
                        "per_rank_host_issue_ms_per_step": [round(1e3 * float(t) / K, 4) for t in issue_all[:, 0]],
                        "per_rank_e2e_ms_per_step": [round(1e3 * float(t) / K, 3) for t in issue_all[:, 1]]},
-            "clocks": sampler.summary([(t_w0, t_w1), (t_e0, t_e1)]),
+            "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_b), "d2h_bytes_per_step": int(out_b),
                     "ms_per_step": 1e3 * e2e_max / K, "api": "sonicsim_b200.render.Renderer.plan_host(...).run() -> ss_render_host",
                     "bit_identical_to_device_arm": same, "checksum": checksum},
@@ -292,7 +307,7 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                          "limiter": "fp32 issue + shared-memory/barrier latency, not DRAM (see DESIGN.md section 4)",
-                         "ncu_k_render": ncu_extra,
+                         "ncu_k_render": ncu_extra, "issue": issue,
                          "alg_bytes_per_launch": alg_per_launch, "kernel_ms": 1e3 * k_render_s,
                          "k_prepare_ms": 1e3 * k_spec_s, "path_achieved": achieved_path,
                          "path_frac": achieved_path / peak, "launch_pairs_timed": int(n_pairs),
