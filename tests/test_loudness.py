@@ -137,3 +137,28 @@ def test_relative_gate_known_answer(emu):
     assert abs(got - ref) < 1e-4
     # without the relative gate the answer would be the mean power of both halves, ~ -26.0: the gate matters
     assert ref > -24.0
+
+
+def test_oracle_loudness_close_to_torchaudio_bs1770():
+    """Independent implementation of the same recommendation (torchaudio.functional.loudness, BS.1770-4): the
+    oracle's restatement of pyloudnorm agrees with it within 0.3 LU on programme material with silent gaps and
+    level steps, where the two gates matter (without gating the same signals read > 1 LU lower).  This is a sanity
+    bound, not the pin - pyloudnorm's filter coefficients differ slightly from torchaudio's."""
+    import torch
+    import torchaudio
+    from scipy import signal
+    rng = np.random.default_rng(1)
+    for sr, C in [(16000, 1), (16000, 2), (48000, 2)]:
+        segs = []
+        for lvl, dur in [(0.2, 2.0), (0.0, 1.5), (0.003, 2.0), (0.1, 1.0), (0.0, 0.7), (0.3, 1.3)]:
+            n = int(sr * dur)
+            segs.append(rng.standard_normal((n, C)) * lvl + (lvl * 0.5) * np.sin(2 * np.pi * 300 * np.arange(n) / sr)[:, None])
+        x = np.concatenate(segs).astype(np.float64)
+        ours = so.bs1770_integrated_loudness(x, sr)
+        theirs = torchaudio.functional.loudness(torch.from_numpy(x.T.copy()).float(), sr).item()
+        assert abs(ours - theirs) < 0.3, (sr, C, ours, theirs)
+        y = x.copy()
+        for b, a in so.bs1770_k_weighting(sr):
+            y = signal.lfilter(b, a, y, axis=0)
+        ungated = -0.691 + 10.0 * np.log10(np.sum(np.mean(y ** 2, axis=0)))
+        assert theirs - ungated > 1.0, (sr, C, ungated, theirs)
