@@ -179,6 +179,12 @@ void ss_reset_stats(ss_ctx* ctx);
 int ss_set_profiling(ss_ctx* ctx, int on);
 int ss_get_profile(ss_ctx* ctx, double* ms_spectra, double* ms_render, int64_t* n_pairs);
 
+/* Test hook, pure host code (no CUDA call): the blocking plan of one source whose trajectory bounds are on the host
+ * (`bounds_host`): blocks_out receives (start, len, p_lo, p_hi) per block, *aligned_out whether the blocks follow
+ * the trajectory's waypoints (one transform each) or the 4096-sample grid.  Returns the number of blocks, or a
+ * negative ss_status (SS_ERR_NOMEM: max_blocks too small). */
+int ss_debug_plan(const ss_source* item, int32_t* blocks_out, int32_t max_blocks, int32_t* aligned_out);
+
 /* pinned host memory helpers (cudaHostAlloc) for callers without torch */
 int ss_host_alloc(void** ptr, int64_t bytes);
 void ss_host_free(void* ptr);

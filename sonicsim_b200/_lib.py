@@ -122,6 +122,7 @@ def load():
         lib.ss_mix_host_ex.argtypes = [vp, vp, vp, vp, ctypes.c_float, vp, vp, i32, i32, i64, i32]
         lib.ss_overlap_dev.argtypes = [vp, vp, vp, i32, i64, i64, vp]
         lib.ss_overlap_host.argtypes = [vp, vp, vp, i32, i64, i64]
+        lib.ss_debug_plan.argtypes = [ctypes.POINTER(SsSource), vp, i32, ctypes.POINTER(i32)]
         lib.ss_launch_count.argtypes = [vp]
         lib.ss_launch_count.restype = i64
         lib.ss_reset_stats.argtypes = [vp]
@@ -139,7 +140,7 @@ def load():
 EXPORTS = ["ss_version", "ss_strerror", "ss_last_cuda_error", "ss_create", "ss_destroy",
            "ss_set_chunk_bytes", "ss_render_dev", "ss_render_host", "ss_render_host_ex", "ss_convolve_fixed_receiver",
            "ss_convolve_moving_receiver", "ss_loudness_dev", "ss_lufs_norm_host", "ss_mix_scratch_doubles", "ss_mix_dev", "ss_mix_host",
-           "ss_mix_host_ex", "ss_overlap_dev", "ss_overlap_host", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
+           "ss_mix_host_ex", "ss_overlap_dev", "ss_overlap_host", "ss_debug_plan", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
            "ss_host_free"]
 
 

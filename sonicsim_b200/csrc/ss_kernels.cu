@@ -579,6 +579,26 @@ static int build_blocks_host(const ss_source& it, const Shape& sh, const int32_t
     return nblk;
 }
 
+// Test hook (pure host, no CUDA call): the blocking plan the library would use for `item` - the choice between
+// waypoint-aligned and 4096-grid blocking and the block table of the host-built path.  blocks_out receives
+// (start, len, p_lo, p_hi) per block in use; returns their number or a negative ss_status.
+extern "C" int ss_debug_plan(const ss_source* item, int32_t* blocks_out, int32_t max_blocks, int32_t* aligned_out) {
+    if (!item || !blocks_out || max_blocks < 0) return SS_ERR_INVALID;
+    if (item->N <= 0 || item->C <= 0 || item->L <= 0 || item->P <= 0) return SS_ERR_INVALID;
+    if (item->mode == SS_MOVING_BOUNDS && (!item->bounds_host || item->P < 2)) return SS_ERR_INVALID;
+    const Shape sh = shape_of(*item);
+    if (sh.nblk_max > max_blocks) return SS_ERR_NOMEM;
+    std::vector<Block> blocks((size_t)sh.nblk_max);
+    std::vector<double> rstep((size_t)item->P);
+    const int nblk = build_blocks_host(*item, sh, item->bounds_host, blocks.data(), rstep.data());
+    for (int i = 0; i < nblk; ++i) {
+        blocks_out[4 * i] = blocks[i].start; blocks_out[4 * i + 1] = blocks[i].len;
+        blocks_out[4 * i + 2] = blocks[i].p_lo; blocks_out[4 * i + 3] = blocks[i].p_hi;
+    }
+    if (aligned_out) *aligned_out = sh.aligned;
+    return nblk;
+}
+
 // Enqueue the three launches for items[first, last) (device pointers) on `stream`.
 static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, cudaStream_t stream, int buf = 0) {
     const int n = last - first;

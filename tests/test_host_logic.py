@@ -93,3 +93,59 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
         assert got[(cname, "size")] == ctypes.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
+def _plan(N, P, C, L, bounds):
+    """ss_debug_plan through ctypes: (blocks (n, 4), aligned)."""
+    lib = _lib.load()
+    b = np.ascontiguousarray(bounds, dtype=np.int32)
+    item = _lib.SsSource(x=1, rir=1, out=1, bounds=b.ctypes.data, N=N, P=P, C=C, L=L, mode=_lib.SS_MOVING_BOUNDS,
+                         bounds_host=b.ctypes.data)
+    cap = (N + 4095) // 4096 + P
+    out = np.zeros((cap, 4), dtype=np.int32)
+    aligned = ctypes.c_int32(-1)
+    n = lib.ss_debug_plan(ctypes.byref(item), out.ctypes.data, cap, ctypes.byref(aligned))
+    assert n >= 0, n
+    return out[:n], aligned.value
+
+
+def test_host_block_planner_invariants_and_choice():
+    """The host twin of k_blocks (build_blocks_host / choose_aligned in ss_kernels.cu, pure host code): blocks tile
+    [0, N) exactly, never exceed 4096 samples, never cross a waypoint under aligned blocking and carry that segment's
+    position pair; the plan chosen is the one with fewer inverse transforms (exact counts from the bounds)."""
+    rng = np.random.default_rng(5)
+    for case in range(200):
+        P = int(rng.integers(2, 70))
+        N = int(rng.integers(P, 200000))
+        cuts = np.sort(rng.integers(0, N + 1, P - 2)) if rng.random() < 0.8 else np.sort(rng.choice([0, N // 2, N], P - 2))
+        bounds = np.concatenate([[0], cuts, [N]]).astype(np.int32)          # zero-length segments allowed
+        L = int(rng.choice([1, 300, 4096, 4097, 9000]))
+        blocks, aligned = _plan(N, P, 2, L, bounds)
+        # exact transform counts of the two plans
+        seg = np.diff(bounds.astype(np.int64))
+        cost_aligned = int(np.sum((seg + 4095) // 4096))
+        cost_grid = 0
+        for b0 in range(0, N, 4096):
+            n0, n1 = b0, min(b0 + 4096, N) - 1
+            lo = int(np.searchsorted(bounds[1:], n0, side="right"))          # segment of the first sample
+            hi = int(np.searchsorted(bounds[1:], n1, side="right"))          # ... of the last one
+            lo, hi = min(lo, P - 2), min(hi, P - 2)
+            cost_grid += (hi - lo + 2 + 1) // 2
+        if L > 4096:
+            assert aligned == 0                                              # long RIRs stay on the grid
+        else:
+            assert aligned == (1 if cost_aligned <= cost_grid else 0), (case, cost_aligned, cost_grid)
+        # tiling
+        order = np.argsort(blocks[:, 0], kind="stable")
+        pos = 0
+        for s, ln, p_lo, p_hi in blocks[order]:
+            assert s == pos and 0 < ln <= 4096
+            pos += ln
+            if aligned:
+                assert p_hi == p_lo + 1 and bounds[p_lo] <= s and s + ln <= bounds[p_lo + 1]
+                assert (s - bounds[p_lo]) % 4096 == 0
+            else:
+                assert s % 4096 == 0
+        assert pos == N
+        if aligned:
+            assert len(blocks) == cost_aligned
