@@ -18,7 +18,9 @@ from .SonicSim_moving import _as_f32, _samples_per_interval, bounds_from_counts
 class MovingSource(T.NamedTuple):
     """One moving source: dry (N,), RIRs (P, C, L), trajectory as int32 segment bounds (P,).
     `bounds_host` (device path only, optional): NumPy copy of `bounds`; lets the library build the block
-    table on the host instead of launching one more small kernel."""
+    table on the host (exact choice of the blocking plan, one small kernel less).  It must hold the same values as
+    the device tensor whenever the batch runs - a plan that is re-run after `bounds` was overwritten on the device
+    needs a new plan (or no `bounds_host`)."""
     dry: T.Any
     rirs: T.Any
     bounds: T.Any
