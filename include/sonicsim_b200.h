@@ -78,9 +78,27 @@ void ss_destroy(ss_ctx* ctx);
 int ss_set_chunk_bytes(ss_ctx* ctx, int64_t bytes);
 
 /* Replaces SonicSim_moving.convolve_moving_receiver (SonicSim_moving.py:63-96) and
- * convolve_fixed_receiver (:47-61) for a whole batch of sources in three kernel launches per
- * chunk.  Device pointers; asynchronous on `stream`. */
+ * convolve_fixed_receiver (:47-61) for a whole batch of sources in two (three without bounds_host) kernel
+ * launches per chunk.  Device pointers; asynchronous on `stream`.
+ * Preconditions the device path cannot check without a round trip (the host path checks them and returns
+ * SS_ERR_INDEX / SS_ERR_INVALID like the reference raises): SS_MOVING_INDEXED: 0 <= idx[n] <= P - 2 for every n
+ * (out-of-range samples are rendered as zeros, not reported); SS_MOVING_BOUNDS without bounds_host: bounds is
+ * non-decreasing with bounds[0] = 0 and bounds[P - 1] = N (anything else is undefined behaviour). */
 int ss_render_dev(ss_ctx* ctx, const ss_source* items, int n_items, void* stream);
+
+/* A batch of device-resident sources bound once (the generation loop of SonicSet.py:180-214 renders the same
+ * shapes scene after scene into the same buffers).  ss_plan_create validates, chunks, builds the block tables and
+ * keeps the descriptor blocks and the scratch for the spectra resident; ss_plan_run is then kernel launches only,
+ * issued as ONE CUDA graph launch on `stream` (captured on the first run; the launches fork over the context's
+ * internal streams and join back).  Results are identical to ss_render_dev on the same items.  The pointers in
+ * `items` and the values behind bounds_host must stay valid and unchanged while the plan lives; the contents of the
+ * x / rir / out buffers may change between runs.  Device-side `bounds` / `idx` are read at run time and must satisfy the
+ * same preconditions as for ss_render_dev.  Not thread-safe; destroy plans before their context. */
+typedef struct ss_plan ss_plan;
+int ss_plan_create(ss_ctx* ctx, const ss_source* items, int n_items, ss_plan** out);
+int ss_plan_run(ss_plan* plan, void* stream);
+int ss_plan_is_graph(const ss_plan* plan);     /* 1 once the plan runs as an instantiated CUDA graph */
+void ss_plan_destroy(ss_plan* plan);
 
 /* Same, host pointers: H2D -> render -> D2H, pipelined over chunks on internal streams.  Returns
  * when every `out` is complete.  This is what the drop-in Python functions call. */

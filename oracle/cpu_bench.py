@@ -1,9 +1,15 @@
-"""Timing harness for the CPU reference path (the oracle port, which makes the same scipy calls as
-SonicSim_moving.py:86-94 and therefore has the reference's cost).  TEST / BENCH INFRASTRUCTURE:
-used only by bench.py's `cpu_baseline` leg and `--impl reference` arm.
+"""Timing harness for the reference's CPU path.  TEST / BENCH INFRASTRUCTURE: used only by bench.py's
+`cpu_baseline` leg and `--impl reference` arm.
 
-One worker process per host core, each rendering whole (utterance, source) units single-threaded
-(the reference never sets scipy's `workers`), as SURVEY 8(d)(ii) prescribes.
+What is timed: `convolve_moving_receiver` (SonicSim_moving.py:63-96) on whole BASELINE configs[1] sources -
+the UNMODIFIED reference module from oracle/_ref when oracle/build_ref.py has put it there (kind "reference"),
+otherwise the oracle port, which makes the same scipy calls (kind "port").
+
+One worker process per host core, each rendering whole (utterance, source) units single-threaded (the
+reference never sets scipy's `workers`), as SURVEY 8(d)(ii) prescribes.  Every worker has its own command
+pipe, so a batch can address exactly the first W workers: the number of concurrently active workers is
+calibrated (the path allocates ~1.4 GB of temporaries per unit and stops scaling long before 128 processes),
+never the length of the signal.
 """
 import os
 import time
@@ -23,37 +29,61 @@ def cfg2_source(seed, P=40, C=6, L=4096, N=480000):
     return x, h, idx, w
 
 
-_cache = {}
+def reference_kind():
+    from oracle import build_ref
+    return "reference" if build_ref.available() else "port"
 
 
-def _worker(args):
-    seed, shape, reps = args[:3]
-    n_samples = args[3] if len(args) > 3 else None
+def _render_fn():
+    """The function under test: the unmodified reference if oracle/_ref holds it, else the oracle port."""
+    from oracle import build_ref
+    ref = build_ref.load()
+    if ref is not None:
+        return ref.convolve_moving_receiver, "reference"
+    from oracle import sonicsim_oracle as so
+    return so.convolve_moving_receiver, "port"
+
+
+def _worker_main(conn, seed, shape):
     for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[k] = "1"
-    from oracle import sonicsim_oracle as so
-    key = (seed,) + tuple(shape)
-    if key not in _cache:
-        _cache.clear()
-        _cache[key] = cfg2_source(seed, *shape)
-    x, h, idx, w = _cache[key]
-    if n_samples is not None and n_samples < x.shape[0]:      # bounded sample: the first n_samples of the unit
-        x, idx, w = x[:n_samples], idx[:n_samples], w[:n_samples]
-    t0 = time.perf_counter()
-    acc = 0.0
-    for _ in range(reps):
-        y = so.convolve_moving_receiver(x, h, idx, w)
-        acc += float(y[0, -1])
-    return time.perf_counter() - t0, acc
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+    fn, kind = _render_fn()
+    x, h, idx, w = cfg2_source(seed, *shape)
+    conn.send(("ready", kind))
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            break
+        reps, n_samples = msg
+        xs, ids, ws = x, idx, w
+        if n_samples is not None and n_samples < x.shape[0]:
+            xs, ids, ws = x[:n_samples], idx[:n_samples], w[:n_samples]
+        t0 = time.perf_counter()
+        acc = 0.0
+        for _ in range(reps):
+            y = fn(xs, h, ids, ws)
+            acc += float(np.asarray(y)[0, -1])
+        conn.send((time.perf_counter() - t0, acc))
+    conn.close()
 
 
-def pick_workers(shape=(40, 6, 4096, 480000)):
-    """Workers = host cores, capped by memory: one unit needs ~ (P*C*N*4 B) * 3 of temporaries."""
+def host_cores():
     cores = os.cpu_count() or 1
     try:
         cores = len(os.sched_getaffinity(0))
     except Exception:
         pass
+    return cores
+
+
+def pick_workers(shape=(40, 6, 4096, 480000)):
+    """Workers = host cores, capped by memory: one unit needs ~ (P*C*N*4 B) * 3 of temporaries."""
+    cores = host_cores()
     P, C, L, N = shape
     per = 3.0 * P * C * (N + L) * 4 + 1e9
     try:
@@ -66,32 +96,75 @@ def pick_workers(shape=(40, 6, 4096, 480000)):
 
 
 class CpuPool:
-    """Persistent spawn-pool so that imports and input synthesis stay outside the timed region."""
+    """Persistent spawned workers, one pipe each; imports and input synthesis stay outside every timed region."""
 
     def __init__(self, workers=None, shape=(40, 6, 4096, 480000)):
         import multiprocessing as mp
+        ctx = mp.get_context("spawn")
         self.shape = shape
         self.workers = workers or pick_workers(shape)
-        self.pool = mp.get_context("spawn").Pool(self.workers)
-        # warm-up: import scipy, synthesise each worker's unit (untimed), then one timed full-size batch
-        self.pool.map(_worker, [(2000 + i, shape, 1, 4 * shape[2]) for i in range(self.workers)], chunksize=1)
-        t0 = time.perf_counter()
-        self.pool.map(_worker, [(2000 + i, shape, 1) for i in range(self.workers)], chunksize=1)
-        self.t_full = time.perf_counter() - t0
+        self.conns, self.procs = [], []
+        for i in range(self.workers):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_worker_main, args=(b, 2000 + i, shape), daemon=True)
+            p.start()
+            b.close()
+            self.conns.append(a)
+            self.procs.append(p)
+        self.kind = "port"
+        for c in self.conns:
+            self.kind = c.recv()[1]
+        self.run_batch(1, 4 * shape[2])                       # warm-up: scipy plans, allocator
+        self.active = self.workers
 
-    def run_batch(self, reps=1, n_samples=None):
-        """Every worker renders (the first n_samples of) its unit `reps` times.  Returns (wall seconds, units)."""
+    def run_batch(self, reps=1, n_samples=None, active=None):
+        """The first `active` workers each render (the first n_samples of) their unit `reps` times, concurrently.
+        Returns (wall seconds, units rendered)."""
+        n = min(active or self.workers, self.workers)
         t0 = time.perf_counter()
-        self.pool.map(_worker, [(2000 + i, self.shape, reps, n_samples) for i in range(self.workers)], chunksize=1)
-        return time.perf_counter() - t0, self.workers * reps
+        for c in self.conns[:n]:
+            c.send((reps, n_samples))
+        for c in self.conns[:n]:
+            c.recv()
+        return time.perf_counter() - t0, n * reps
+
+    def calibrate(self, budget_s=60.0):
+        """Full-size batches at W = cores, cores/2, ...: pick the worker count with the highest throughput.
+        Returns [(W, seconds per batch)], best first; self.active is set to the best W."""
+        tried, w = [], self.workers
+        t_used = 0.0
+        while w >= 1:
+            t, units = self.run_batch(1, None, w)
+            tried.append((w, t))
+            t_used += t
+            if w == 1 or t_used > budget_s:
+                break
+            # halving the workers can at best keep the batch time: stop when throughput has clearly dropped
+            if len(tried) >= 2 and tried[-1][0] / tried[-1][1] < 0.7 * max(a / b for a, b in tried):
+                break
+            w //= 2
+        tried.sort(key=lambda ab: -(ab[0] / ab[1]))
+        self.active = tried[0][0]
+        return tried
 
     def close(self):
-        self.pool.close()
-        self.pool.join()
+        for c in self.conns:
+            try:
+                c.send(None)
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.kill()                                       # exact PID of a process this pool started
 
 
 def single_thread_time(shape=(40, 6, 4096, 480000), reps=2):
-    """The reference exactly as shipped: one process, one thread."""
-    _worker((2000, shape, 1))
-    t, _ = _worker((2000, shape, reps))
-    return t / reps
+    """The reference exactly as shipped: one process, one thread (run in this process)."""
+    fn, _ = _render_fn()
+    x, h, idx, w = cfg2_source(2000, *shape)
+    fn(x, h, idx, w)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn(x, h, idx, w)
+    return (time.perf_counter() - t0) / reps

@@ -108,6 +108,11 @@ def load():
         lib.ss_destroy.restype = None
         lib.ss_set_chunk_bytes.argtypes = [vp, i64]
         lib.ss_render_dev.argtypes = [vp, ctypes.POINTER(SsSource), ctypes.c_int, vp]
+        lib.ss_plan_create.argtypes = [vp, ctypes.POINTER(SsSource), ctypes.c_int, ctypes.POINTER(vp)]
+        lib.ss_plan_run.argtypes = [vp, vp]
+        lib.ss_plan_is_graph.argtypes = [vp]
+        lib.ss_plan_destroy.argtypes = [vp]
+        lib.ss_plan_destroy.restype = None
         lib.ss_render_host.argtypes = [vp, ctypes.POINTER(SsSource), ctypes.c_int]
         lib.ss_render_host_ex.argtypes = [vp, ctypes.POINTER(SsSource), ctypes.c_int, ctypes.POINTER(SsPostLufs)]
         lib.ss_convolve_fixed_receiver.argtypes = [vp, vp, vp, vp, i32, i32, i32]
@@ -138,7 +143,7 @@ def load():
 
 
 EXPORTS = ["ss_version", "ss_strerror", "ss_last_cuda_error", "ss_create", "ss_destroy",
-           "ss_set_chunk_bytes", "ss_render_dev", "ss_render_host", "ss_render_host_ex", "ss_convolve_fixed_receiver",
+           "ss_set_chunk_bytes", "ss_render_dev", "ss_plan_create", "ss_plan_run", "ss_plan_is_graph", "ss_plan_destroy", "ss_render_host", "ss_render_host_ex", "ss_convolve_fixed_receiver",
            "ss_convolve_moving_receiver", "ss_loudness_dev", "ss_lufs_norm_host", "ss_mix_scratch_doubles", "ss_mix_dev", "ss_mix_host",
            "ss_mix_host_ex", "ss_overlap_dev", "ss_overlap_host", "ss_debug_plan", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
            "ss_host_free"]

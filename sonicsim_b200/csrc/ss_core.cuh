@@ -158,18 +158,28 @@ SS_HD void fft16(float2 (&v)[16]) {
     for (int b = 0; b < 4; ++b) fft4<INV>(v[b], v[b + 4], v[b + 8], v[b + 12]);
     fft16_level2<INV>(v);
 }
-// the same with the inter-pass twiddles v[r] *= tab[r * STRIDE], r = 1..15, folded into the first level
+// the same with the inter-pass twiddles v[r] *= w[r], r = 1..15, folded into the first level.  The twiddles of a
+// thread's two butterflies of a pass (j and j + 256) are the same, and they do not depend on the data: tw_load can be
+// issued ahead of the barrier that guards the pass's inputs.
 template <bool INV, int STRIDE>
-SS_HD void fft16_tw(float2 (&v)[16], const float2* tab) {
-    float2 w[16];
+SS_HD void tw_load(const float2* tab, float2 (&w)[16]) {
     w[0] = make_float2(1.f, 0.f);
 #pragma unroll
     for (int r = 1; r < 16; ++r)
         w[r] = dirw<INV>((STRIDE == 256 && r >= SS_TWC_STREAM_FROM) ? ldg_stream(tab + r * STRIDE) : ldg_cached(tab + r * STRIDE));
+}
+template <bool INV>
+SS_HD void fft16_w(float2 (&v)[16], const float2 (&w)[16]) {
     fft4_tw<INV, false>(v[0], v[4], v[8], v[12], w[0], w[4], w[8], w[12]);
 #pragma unroll
     for (int b = 1; b < 4; ++b) fft4_tw<INV, true>(v[b], v[b + 4], v[b + 8], v[b + 12], w[b], w[b + 4], w[b + 8], w[b + 12]);
     fft16_level2<INV>(v);
+}
+template <bool INV, int STRIDE>
+SS_HD void fft16_tw(float2 (&v)[16], const float2* tab) {
+    float2 w[16];
+    tw_load<INV, STRIDE>(tab, w);
+    fft16_w<INV>(v, w);
 }
 // register slot that holds output index r after fft16
 SS_HD constexpr int out16(int r) { return 4 * (r & 3) + (r >> 2); }

@@ -36,6 +36,7 @@ struct ss_ctx {
     int64_t launches = 0;
     bool single_stream = false;   // experiment knob (SS_SINGLE_STREAM=1): no chunk overlap
     bool no_fast = false;         // experiment knob (SS_NO_FAST=1): never pick the all-aligned kernel variant
+    bool no_graph = false;        // experiment knob (SS_NO_GRAPH=1): plans enqueue their launches instead of a CUDA graph
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Prof { cudaEvent_t e0, e1, e2; int chunk; };   // chunk = position of the launch pair inside its render call

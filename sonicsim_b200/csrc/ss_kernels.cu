@@ -341,6 +341,210 @@ k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr, i
     }
 }
 
+// ----------------------------------------------------------------------------- k_render_fast
+// The all-aligned chunk (every source a compact trajectory with L <= 4096: BASELINE configs[1] / [2]): one item = one
+// transform that packs the positions (s, s + 1) of the block's segment.  Same phases as k_render; what differs is how
+// the 8 warps of a CTA synchronise and who feeds the bulk-copy engine:
+//   * two CTA-wide barriers per transform (pass A -> B and pass B -> C exchanges through the FFT buffer).  The two
+//     write-after-read hazards of the in-place buffer (staged spectra -> pass-A stores, pass-B loads -> pass-B stores)
+//     are split barriers: a warp *arrives* on an mbarrier as soon as its loads are done, computes its two radix-16
+//     butterflies, and only then waits - by which time the other warps have normally arrived;
+//   * no serial producer section.  Work items are final (k_prepare wrote pointers, sample range, segment start and
+//     1 / length), prefetched two transforms ahead by one lane with cp.async.  The copy of the next transform's X / Hp
+//     into the FFT buffer is issued by whichever warp is the LAST to finish its pass-C loads (a shared counter tells),
+//     so nobody waits for the buffer to drain; its Hq copy by one lane right after the first split barrier;
+//   * the 15 inter-pass twiddles of passes B and C are the same for both butterflies of a thread and independent of
+//     the data: they are loaded ahead of the CTA-wide barrier, while the 64 data registers are dead.
+constexpr int kItemLane = 7 * 32;     // thread that prefetches work items and issues the Hq copies (not warp 0, whose
+                                      // thread 0 already carries the DC / Nyquist words)
+// experiment knobs (profiles/EXPERIMENTS.md, round 2)
+#ifndef SS_F_SPLIT
+#define SS_F_SPLIT 0          // 1: split (arrive early / wait late) mbarriers instead of two of the CTA-wide barriers
+#endif
+#ifndef SS_F_HOIST
+#define SS_F_HOIST 0          // 1: inter-pass twiddles loaded ahead of the exchange barrier
+#endif
+#ifndef SS_F_FENCEALL
+#define SS_F_FENCEALL 0       // 1: every thread fences generic -> async proxy before the FFT buffer is handed over
+#endif
+#ifndef SS_F_LATECHECK
+#define SS_F_LATECHECK 0      // 1: the last-warp test (and the X / Hp copy) after the first pass-C butterfly
+#endif
+#ifndef SS_F_FAKE
+#define SS_F_FAKE 0           // timing experiments only (WRONG results): 1 no pass B, 2 no staged-spectra reads, 4 no global stores, 8 no bulk copies
+#endif
+#ifndef SS_F_WAITHINT
+#define SS_F_WAITHINT 0       // > 0: suspend-time hint (ns) of the split barriers' try_wait
+#endif
+__device__ __forceinline__ unsigned atom_inc_acqrel(unsigned* p) {
+    unsigned old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+    return old;
+}
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
+#if SS_F_WAITHINT > 0
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SS_F_WAITHINT) : "memory");
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+// both butterflies of a thread, the 16 loads of butterfly t first so that its arithmetic can start while the
+// loads of butterfly t + 256 are still in flight
+__device__ __forceinline__ void load2_ab(int t, const float2* s, Regs32& R) {
+    const float2* p = s + pad(t);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) R.a[r] = p[544 * r];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) R.b[r] = p[544 * r + 272];
+}
+__global__ void __launch_bounds__(kThreads, SS_RENDER_MINB)
+k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr, int n_items_host) {
+    extern __shared__ __align__(128) float2 smem[];
+    __shared__ __align__(16) RItem s_item[3];
+    __shared__ __align__(8) uint64_t s_bar[4];          // [0] X + Hp landed, [1] Hq landed (transaction counts);
+                                                        // [2] staged spectra consumed, [3] pass-B inputs loaded (8 warps)
+    __shared__ unsigned s_drained;                      // warps that have finished their pass-C loads, cumulative
+    float2* const fftbuf = smem;
+    float2* const sX = smem;
+    float2* const sHp = smem + kSpec;
+    float2* const sHq = smem + kPadF;
+    const Tables T{g_tw, g_twB, g_twC};
+    const int t = threadIdx.x, lane = t & 31;
+    const int grid = (int)gridDim.x;
+    // table length: known on the host when it built the tables, otherwise written by k_blocks
+    const int n_items = n_items_host >= 0 ? n_items_host : *n_items_ptr;
+    const int n_k = (n_items - (int)blockIdx.x + grid - 1) / grid;      // transforms of this CTA
+    if (n_k <= 0) return;
+    const RItem* const my_items = items + blockIdx.x;
+
+    if (t == kItemLane) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar[2], kThreads / 32);
+        mbar_init(&s_bar[3], kThreads / 32);
+        s_drained = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_item[0] = my_items[0];
+        if (n_k > 1) s_item[1] = my_items[grid];
+        const float2* const hp = s_item[0].H0 + (size_t)s_item[0].p_lo * s_item[0].pstride;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
+        bulk_g2s(sX, s_item[0].X, kSpecBytes, &s_bar[0]);
+        bulk_g2s(sHp, hp, kSpecBytes, &s_bar[0]);
+        mbar_expect_tx(&s_bar[1], kSpecBytes);
+        bulk_g2s(sHq, hp + s_item[0].pstride, kSpecBytes, &s_bar[1]);
+    }
+    __syncthreads();
+
+    Regs32 R;
+    float2 w[16];
+    XDesc unused; unused.kparts = 1; unused.Hq = nullptr; unused.X = nullptr; unused.Hp = nullptr;
+    unsigned ph = 0;
+    for (int k = 0; k < n_k; ++k) {
+#if !(SS_F_FAKE & 8)
+        mbar_wait(&s_bar[0], ph);
+        mbar_wait(&s_bar[1], ph);
+#endif
+#if SS_F_FAKE & 2
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { R.a[r] = make_float2(1.f + r + t, 2.f * r - k); R.b[r] = make_float2(0.5f * r + k, 3.f - t); }
+#else
+        form_z<false, true>(t, sX, sHp, sHq, unused, R);
+#endif
+#if SS_F_SPLIT
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_bar[2]);            // this warp no longer reads the staged spectra
+        fft16<true>(R.a);
+        fft16<true>(R.b);
+        mbar_wait_hint(&s_bar[2], ph);                    // ... and neither does any other: pass A may overwrite X / Hp
+#else
+        fft16<true>(R.a);
+        fft16<true>(R.b);
+        __syncthreads();
+#endif
+        if (t == kItemLane) {
+            if (k + 1 < n_k && !(SS_F_FAKE & 8)) {        // Hq of transform k + 1 (its item became visible at barrier B4 of k - 1)
+                const RItem& nx = s_item[(k + 1) % 3];
+                fence_proxy_async();
+                mbar_expect_tx(&s_bar[1], kSpecBytes);
+                bulk_g2s(sHq, nx.H0 + (size_t)(nx.p_lo + 1) * nx.pstride, kSpecBytes, &s_bar[1]);
+            }
+            // item k + 2 into the slot of item k - 1 (last read in the output stage of k - 1, which every warp has left)
+            if (k + 2 < n_k) item_prefetch(&s_item[(k + 2) % 3], my_items + (size_t)(k + 2) * grid);
+        }
+        passA_store(fftbuf, passA_jA(t), R.a);
+        passA_store(fftbuf, passA_jB(t), R.b);
+#if SS_F_HOIST
+        tw_load<true, 16>(T.twB + (t & 15), w);
+#endif
+#if !(SS_F_FAKE & 1)
+        __syncthreads();                                  // B2: pass A -> pass B exchange
+        load2_ab(t, fftbuf, R);
+#if !SS_F_HOIST
+        tw_load<true, 16>(T.twB + (t & 15), w);
+#endif
+#if SS_F_SPLIT
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_bar[3]);
+        fft16_w<true>(R.a, w);
+        fft16_w<true>(R.b, w);
+        mbar_wait_hint(&s_bar[3], ph);                    // every warp has loaded its pass-B inputs
+#else
+        fft16_w<true>(R.a, w);
+        fft16_w<true>(R.b, w);
+        __syncthreads();
+#endif
+        passB_store(fftbuf, t, R.a);
+        passB_store(fftbuf, t + 256, R.b);
+#endif
+#if SS_F_HOIST
+        tw_load<true, 256>(T.twC + t, w);
+#endif
+        if (t == kItemLane) item_prefetch_wait();         // item k + 2 has landed; visible to all behind B4
+        __syncthreads();                                  // B4: pass B -> pass C exchange
+        load2_ab(t, fftbuf, R);
+#if !SS_F_HOIST
+        tw_load<true, 256>(T.twC + t, w);
+#endif
+#if SS_F_FENCEALL
+        fence_proxy_async();
+#endif
+        __syncwarp();
+        unsigned drained = 0;
+        if (lane == 0) drained = atom_inc_acqrel(&s_drained);
+#if SS_F_LATECHECK
+        fft16_w<true>(R.a, w);                            // pass C, first butterfly
+#endif
+        if (lane == 0 && drained == (unsigned)(8 * k + 7) && k + 1 < n_k && !(SS_F_FAKE & 8)) {
+            // last warp out of the FFT buffer: stage X, Hp of transform k + 1 into it
+            const RItem& nx = s_item[(k + 1) % 3];
+            fence_proxy_async();
+            mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
+            bulk_g2s(sX, nx.X, kSpecBytes, &s_bar[0]);
+            bulk_g2s(sHp, nx.H0 + (size_t)nx.p_lo * nx.pstride, kSpecBytes, &s_bar[0]);
+        }
+        ph ^= 1;
+#if !SS_F_LATECHECK
+        fft16_w<true>(R.a, w);                            // pass C
+#endif
+        fft16_w<true>(R.b, w);
+        render_phase3_close(t, R, T);
+#if SS_F_FAKE & 4
+        if (R.a[0].x + R.a[5].y + R.a[9].x + R.a[15].y == 123.456f) render_epilogue_item(t, s_item[k % 3], R);
+#else
+        render_epilogue_item(t, s_item[k % 3], R);
+#endif
+    }
+}
+
 // ============================================================================= host side
 thread_local int g_last_cuda = 0;
 
@@ -389,7 +593,7 @@ static int init_ctx(ss_ctx* c, int device) {
     CK(cudaFuncSetAttribute(k_prepare<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
     CK(cudaFuncSetAttribute(k_prepare<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
     CK(cudaFuncSetAttribute(k_render<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
-    CK(cudaFuncSetAttribute(k_render<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
+    CK(cudaFuncSetAttribute(k_render_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
     CK(cudaFuncSetAttribute(k_render<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
     for (int i = 0; i < ss_ctx::kRing; ++i) CK(cudaEventCreateWithFlags(&c->desc_ev[i], cudaEventDisableTiming));
     for (int i = 0; i < ss_ctx::kAux; ++i) {
@@ -407,6 +611,7 @@ static int init_ctx(ss_ctx* c, int device) {
     }
     c->single_stream = getenv("SS_SINGLE_STREAM") != nullptr;
     c->no_fast = getenv("SS_NO_FAST") != nullptr;
+    c->no_graph = getenv("SS_NO_GRAPH") != nullptr;
     if (getenv("SS_HOST_CHUNK_MB")) c->chunk_bytes_host = (int64_t)atoi(getenv("SS_HOST_CHUNK_MB")) << 20;
     return SS_OK;
 }
@@ -599,39 +804,49 @@ extern "C" int ss_debug_plan(const ss_source* item, int32_t* blocks_out, int32_t
     return nblk;
 }
 
-// Enqueue the three launches for items[first, last) (device pointers) on `stream`.
-static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, cudaStream_t stream, int buf = 0) {
-    const int n = last - first;
+// ---- one chunk of sources = one (k_blocks,) k_prepare, k_render launch group
+// Everything the launches need besides the descriptor block in device memory.
+struct ChunkLaunch {
+    int n = 0, ps = 0, grid_r = 0, n_known = -1;
+    bool host_tables = true, any_long = false, all_aligned = true;
+    const Source* ds = nullptr; const int* dps = nullptr; RItem* d_items = nullptr; int* d_total = nullptr;
+    PrepParams pp;
+};
+static size_t chunk_scratch_bytes(const ss_source* items, int first, int last) {
     size_t need = 256;
     for (int i = first; i < last; ++i) need += spectra_bytes(items[i]);
-    if (need > c->scratch_cap[buf]) {
-        CK(cudaDeviceSynchronize());
-        if (c->d_scratch[buf]) CK(cudaFree(c->d_scratch[buf]));
-        c->d_scratch[buf] = nullptr; c->scratch_cap[buf] = 0;
-        size_t cap = align_up(need + need / 4, 1 << 20);
-        CK(cudaMalloc(&c->d_scratch[buf], cap));
-        c->scratch_cap[buf] = cap;
-    }
-    // Block tables on the host when every trajectory is host-visible (always true on the host path)
-    bool host_tables = true;
+    return need;
+}
+// Block tables on the host when every trajectory is host-visible (always true on the host path)
+static bool chunk_host_tables(const ss_source* items, int first, int last) {
     for (int i = first; i < last; ++i)
-        if (items[i].mode == SS_MOVING_BOUNDS && !items[i].bounds_host) host_tables = false;
-    // descriptor block: Source[n] | prefix_prepare[n+1] | total | per source: blocks, rstep, counts
-    const size_t off_ps = align_up(sizeof(Source) * n, 16);
-    const size_t off_tot = off_ps + align_up(sizeof(int) * (n + 1), 16);
-    size_t bytes = off_tot + 16;
-    if (host_tables)
+        if (items[i].mode == SS_MOVING_BOUNDS && !items[i].bounds_host) return false;
+    return true;
+}
+// descriptor block: Source[n] | prefix_prepare[n+1] | total | per source: blocks, rstep, counts
+static size_t chunk_desc_bytes(const ss_source* items, int first, int last) {
+    const int n = last - first;
+    size_t bytes = align_up(sizeof(Source) * n, 16) + align_up(sizeof(int) * (n + 1), 16) + 16;
+    if (chunk_host_tables(items, first, last))
         for (int i = first; i < last; ++i) {
             const Shape sh = shape_of(items[i]);
             bytes += align_up(sizeof(Block) * (size_t)sh.nblk_max, 16) + align_up(sizeof(double) * (size_t)items[i].P, 16) + 16;
         }
-    int slot; char *hblk, *dblk;
-    { int st = ring_acquire(c, bytes, &slot, &hblk, &dblk); if (st) return st; }
-    Source* hs = (Source*)c->h_desc[slot];
-    int* hps = (int*)(c->h_desc[slot] + off_ps);
-    char* scratch = c->d_scratch[buf];
+    return bytes;
+}
+// Fill the descriptor block of items[first, last) at `hbase` (host memory) for its device address `dbase`, carve the
+// chunk's spectra / tables / work items out of `scratch` (device), and note the launch parameters in `L`.
+static void chunk_describe(const ss_source* items, int first, int last, char* hbase, char* dbase, char* scratch,
+                           int sm_count, ChunkLaunch* L) {
+    const int n = last - first;
+    const bool host_tables = chunk_host_tables(items, first, last);
+    const size_t off_ps = align_up(sizeof(Source) * n, 16);
+    const size_t off_tot = off_ps + align_up(sizeof(int) * (n + 1), 16);
+    Source* hs = (Source*)hbase;
+    int* hps = (int*)(hbase + off_ps);
     int ps = 0, pr = 0, total_items = 0;
     size_t tab_off = off_tot + 16;
+    bool any_long = false, all_aligned = true;
     for (int i = 0; i < n; ++i) {
         const ss_source& it = items[first + i];
         const Shape sh = shape_of(it);
@@ -647,7 +862,6 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
         s.xspec = (float2*)scratch; scratch += (size_t)s.nblk_max * kSpec * sizeof(float2);
         if (host_tables) {
             // tables live in the descriptor block itself: filled here, copied with it
-            char* hbase = c->h_desc[slot]; char* dbase = c->d_desc[slot];
             Block* hb_blocks = (Block*)(hbase + tab_off);
             s.blocks = (Block*)(dbase + tab_off); tab_off += align_up(sizeof(Block) * (size_t)s.nblk_max, 16);
             double* hb_rstep = (double*)(hbase + tab_off);
@@ -666,50 +880,76 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
         hps[i] = ps;
         ps += spectra_pairs_h(s) + spectra_pairs_x(s) + range_ctas(s);
         pr += sh.max_items;
+        any_long = any_long || s.K > 1; all_aligned = all_aligned && s.aligned;
     }
     hps[n] = ps;
     // work-item table of the whole chunk (dense) + its length
-    RItem* d_items = (RItem*)scratch; scratch += (size_t)pr * sizeof(RItem);
-    int* d_total = host_tables ? (int*)(c->d_desc[slot] + off_tot) : (int*)scratch;
-    if (host_tables) { *(int*)(c->h_desc[slot] + off_tot) = total_items; pr = total_items; }
-    CK(cudaMemcpyAsync(c->d_desc[slot], c->h_desc[slot], bytes, cudaMemcpyHostToDevice, stream));
+    L->d_items = (RItem*)scratch; scratch += (size_t)pr * sizeof(RItem);
+    L->d_total = host_tables ? (int*)(dbase + off_tot) : (int*)scratch;
+    if (host_tables) { *(int*)(hbase + off_tot) = total_items; pr = total_items; }
+    L->n = n; L->ps = ps; L->host_tables = host_tables; L->any_long = any_long; L->all_aligned = all_aligned;
+    L->n_known = host_tables ? total_items : -1;
+    L->grid_r = pr < sm_count * SS_RENDER_MINB ? pr : sm_count * SS_RENDER_MINB;
+    L->ds = (const Source*)dbase;
+    L->dps = (const int*)(dbase + off_ps);
+    L->pp.n_inline = n <= kPrepInline ? n : 0;
+    if (L->pp.n_inline) {
+        memcpy(L->pp.prefix, hps, sizeof(int) * (size_t)(n + 1));
+        memcpy(L->pp.srcs, hs, sizeof(Source) * (size_t)n);
+    }
+}
+// The kernel launches of one described chunk (its descriptor block is, or will be by stream order, in device memory).
+static int chunk_enqueue(ss_ctx* c, const ChunkLaunch& L, cudaStream_t stream, ss_ctx::Prof* pf) {
+    if (pf) CK(cudaEventRecord(pf->e0, stream));
+    if (!L.host_tables) {
+        k_blocks<<<1, 256, 0, stream>>>(L.ds, L.n, L.d_total);
+        CK(cudaGetLastError());
+        c->launches += 1;
+    }
+    if (L.ps > 0) {
+        if (L.pp.n_inline) k_prepare<true><<<L.ps, kThreads, kPadF * (int)sizeof(float2), stream>>>(L.ds, L.dps, L.n, L.d_items, L.pp);
+        else k_prepare<false><<<L.ps, kThreads, kPadF * (int)sizeof(float2), stream>>>(L.ds, L.dps, L.n, L.d_items, L.pp);
+        CK(cudaGetLastError());
+    }
+    if (pf) CK(cudaEventRecord(pf->e1, stream));
+    if (L.grid_r > 0) {
+        if (L.any_long) k_render<true, false><<<L.grid_r, kThreads, kRenderSmem, stream>>>(L.d_items, L.d_total, L.n_known);
+        else if (L.all_aligned && !c->no_fast) k_render_fast<<<L.grid_r, kThreads, kRenderSmem, stream>>>(L.d_items, L.d_total, L.n_known);
+        else k_render<false, false><<<L.grid_r, kThreads, kRenderSmem, stream>>>(L.d_items, L.d_total, L.n_known);
+        CK(cudaGetLastError());
+    }
+    if (pf) CK(cudaEventRecord(pf->e2, stream));
+    c->launches += 2;
+    return SS_OK;
+}
+
+// Describe items[first, last) (device pointers) in the next slot of the descriptor ring, copy the block and enqueue
+// the launches on `stream`.
+static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, cudaStream_t stream, int buf = 0) {
+    const size_t need = chunk_scratch_bytes(items, first, last);
+    if (need > c->scratch_cap[buf]) {
+        CK(cudaDeviceSynchronize());
+        if (c->d_scratch[buf]) CK(cudaFree(c->d_scratch[buf]));
+        c->d_scratch[buf] = nullptr; c->scratch_cap[buf] = 0;
+        size_t cap = align_up(need + need / 4, 1 << 20);
+        CK(cudaMalloc(&c->d_scratch[buf], cap));
+        c->scratch_cap[buf] = cap;
+    }
+    const size_t bytes = chunk_desc_bytes(items, first, last);
+    int slot; char *hblk, *dblk;
+    { int st = ring_acquire(c, bytes, &slot, &hblk, &dblk); if (st) return st; }
+    static thread_local ChunkLaunch L;                  // holds 3.2 KB of kernel parameters: not on the stack
+    chunk_describe(items, first, last, hblk, dblk, c->d_scratch[buf], c->sm_count, &L);
+    CK(cudaMemcpyAsync(dblk, hblk, bytes, cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(c->desc_ev[slot], stream));
-    const Source* ds = (const Source*)c->d_desc[slot];
-    const int* dps = (const int*)(c->d_desc[slot] + off_ps);
     ss_ctx::Prof pf;
     if (c->profiling) {
         CK(cudaEventCreate(&pf.e0)); CK(cudaEventCreate(&pf.e1)); CK(cudaEventCreate(&pf.e2));
         pf.chunk = c->prof_chunk++;
-        CK(cudaEventRecord(pf.e0, stream));
     }
-    if (!host_tables) {
-        k_blocks<<<1, 256, 0, stream>>>(ds, n, d_total);
-        CK(cudaGetLastError());
-        c->launches += 1;
-    }
-    {
-        static thread_local PrepParams pp;             // 3.2 KB: not on the stack
-        pp.n_inline = n <= kPrepInline ? n : 0;
-        if (pp.n_inline) {
-            memcpy(pp.prefix, hps, sizeof(int) * (size_t)(n + 1));
-            memcpy(pp.srcs, hs, sizeof(Source) * (size_t)n);
-        }
-        if (pp.n_inline) k_prepare<true><<<ps, kThreads, kPadF * (int)sizeof(float2), stream>>>(ds, dps, n, d_items, pp);
-        else k_prepare<false><<<ps, kThreads, kPadF * (int)sizeof(float2), stream>>>(ds, dps, n, d_items, pp);
-    }
-    CK(cudaGetLastError());
-    if (c->profiling) CK(cudaEventRecord(pf.e1, stream));
-    const int grid_r = pr < c->sm_count * SS_RENDER_MINB ? pr : c->sm_count * SS_RENDER_MINB;
-    bool any_long = false, all_aligned = true;
-    for (int i = 0; i < n; ++i) { any_long = any_long || hs[i].K > 1; all_aligned = all_aligned && hs[i].aligned; }
-    const int n_known = host_tables ? total_items : -1;
-    if (any_long) k_render<true, false><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total, n_known);
-    else if (all_aligned && !c->no_fast) k_render<false, true><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total, n_known);
-    else k_render<false, false><<<grid_r, kThreads, kRenderSmem, stream>>>(d_items, d_total, n_known);
-    CK(cudaGetLastError());
-    if (c->profiling) { CK(cudaEventRecord(pf.e2, stream)); c->prof.push_back(pf); }
-    c->launches += 2;
-    return SS_OK;
+    const int st = chunk_enqueue(c, L, stream, c->profiling ? &pf : nullptr);
+    if (c->profiling) c->prof.push_back(pf);
+    return st;
 }
 
 // split [0, n) into chunks whose spectra fit the L2-sized budget
@@ -737,10 +977,7 @@ static void make_chunks(const ss_ctx* c, const ss_source* items, int n, std::vec
     cuts.push_back(n);
 }
 
-extern "C" int ss_render_dev(ss_ctx* c, const ss_source* items, int n_items, void* stream) {
-    if (!c || (!items && n_items > 0) || n_items < 0) return SS_ERR_INVALID;
-    if (n_items == 0) return SS_OK;
-    CK(cudaSetDevice(c->device));
+static int validate_dev_items(const ss_source* items, int n_items) {
     for (int i = 0; i < n_items; ++i) {
         int st = validate_item(items[i]); if (st) return st;
         if (items[i].mode == SS_MOVING_BOUNDS && items[i].bounds_host) {
@@ -749,6 +986,14 @@ extern "C" int ss_render_dev(ss_ctx* c, const ss_source* items, int n_items, voi
             for (int q = 0; q + 1 < items[i].P; ++q) if (b[q + 1] < b[q]) return SS_ERR_INVALID;
         }
     }
+    return SS_OK;
+}
+
+extern "C" int ss_render_dev(ss_ctx* c, const ss_source* items, int n_items, void* stream) {
+    if (!c || (!items && n_items > 0) || n_items < 0) return SS_ERR_INVALID;
+    if (n_items == 0) return SS_OK;
+    CK(cudaSetDevice(c->device));
+    { int st = validate_dev_items(items, n_items); if (st) return st; }
     std::vector<int> cuts;
     make_chunks(c, items, n_items, cuts);
     const size_t n_chunks = cuts.size() - 1;
@@ -780,6 +1025,147 @@ extern "C" int ss_render_dev(ss_ctx* c, const ss_source* items, int n_items, voi
     }
     return rc;
 }
+
+// ----------------------------------------------------------------------------- plans (device path)
+// A batch of device-resident sources bound once: validation, chunking, block tables and descriptor blocks are done at
+// creation and stay resident in device memory together with the plan's own scratch, so a run is kernel launches only -
+// captured into a CUDA graph on the first run (fork onto the context's internal streams, join back), one
+// cudaGraphLaunch per run afterwards instead of ~25 runtime calls.  The pointers in `items` (and the contents of
+// bounds_host) must stay valid and unchanged for the plan's life; buffer *contents* may change between runs.
+struct ss_plan {
+    ss_ctx* c = nullptr;
+    std::vector<ChunkLaunch> chunks;
+    char* d_desc = nullptr;
+    char* d_scratch[ss_ctx::kAux] = {};
+    cudaGraphExec_t exec = nullptr;
+    bool graph_failed = false;
+    int launches_per_run = 0;
+    // fork / join events of the plan's own (events recorded while capturing must not be waited on outside the graph,
+    // which the context's events are)
+    cudaEvent_t ev_fork = nullptr, ev_join[ss_ctx::kAux] = {};
+    cudaStream_t s_cap = nullptr;      // capture origin: the caller's stream may be the legacy default stream, which cannot capture
+};
+
+extern "C" void ss_plan_destroy(ss_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->c->device);
+    cudaDeviceSynchronize();
+    if (p->exec) cudaGraphExecDestroy(p->exec);
+    if (p->s_cap) cudaStreamDestroy(p->s_cap);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    for (int i = 0; i < ss_ctx::kAux; ++i) if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
+    if (p->d_desc) cudaFree(p->d_desc);
+    for (int i = 0; i < ss_ctx::kAux; ++i) if (p->d_scratch[i]) cudaFree(p->d_scratch[i]);
+    delete p;
+}
+
+static int plan_build(ss_plan* p, const ss_source* items, int n_items) {
+    ss_ctx* c = p->c;
+    std::vector<int> cuts;
+    make_chunks(c, items, n_items, cuts);
+    const size_t n_chunks = cuts.size() - 1;
+    std::vector<size_t> off(n_chunks + 1, 0);
+    size_t scratch_need[ss_ctx::kAux] = {};
+    for (size_t k = 0; k < n_chunks; ++k) {
+        off[k + 1] = off[k] + align_up(chunk_desc_bytes(items, cuts[k], cuts[k + 1]), 256);
+        const size_t sb = chunk_scratch_bytes(items, cuts[k], cuts[k + 1]);
+        size_t& m = scratch_need[n_chunks < 2 ? 0 : k % ss_ctx::kAux];
+        m = sb > m ? sb : m;
+    }
+    CK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < ss_ctx::kAux; ++i) CK(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&p->s_cap, cudaStreamNonBlocking));
+    CK(cudaMalloc((void**)&p->d_desc, off[n_chunks] + 256));
+    for (int i = 0; i < ss_ctx::kAux; ++i)
+        if (scratch_need[i]) CK(cudaMalloc((void**)&p->d_scratch[i], align_up(scratch_need[i], 1 << 20)));
+    std::vector<char> host(off[n_chunks] + 256);
+    p->chunks.resize(n_chunks);
+    p->launches_per_run = 0;
+    for (size_t k = 0; k < n_chunks; ++k) {
+        chunk_describe(items, cuts[k], cuts[k + 1], host.data() + off[k], p->d_desc + off[k],
+                       p->d_scratch[n_chunks < 2 ? 0 : k % ss_ctx::kAux], c->sm_count, &p->chunks[k]);
+        p->launches_per_run += p->chunks[k].host_tables ? 2 : 3;
+    }
+    CK(cudaMemcpy(p->d_desc, host.data(), off[n_chunks], cudaMemcpyHostToDevice));
+    return SS_OK;
+}
+
+extern "C" int ss_plan_create(ss_ctx* c, const ss_source* items, int n_items, ss_plan** out) {
+    if (!c || !out || !items || n_items <= 0) return SS_ERR_INVALID;
+    *out = nullptr;
+    CK(cudaSetDevice(c->device));
+    { int st = validate_dev_items(items, n_items); if (st) return st; }
+    ss_plan* p = new (std::nothrow) ss_plan();
+    if (!p) return SS_ERR_NOMEM;
+    p->c = c;
+    const int st = plan_build(p, items, n_items);
+    if (st != SS_OK) { ss_plan_destroy(p); return st; }
+    *out = p;
+    return SS_OK;
+}
+
+// the launches of every chunk, forked over the context's internal streams and joined back into `stream`
+static int plan_enqueue(ss_plan* p, cudaStream_t stream) {
+    ss_ctx* c = p->c;
+    const size_t n_chunks = p->chunks.size();
+    if (n_chunks < 2 || c->single_stream) {
+        for (size_t k = 0; k < n_chunks; ++k) { int st = chunk_enqueue(c, p->chunks[k], stream, nullptr); if (st) return st; }
+        return SS_OK;
+    }
+    CK(cudaEventRecord(p->ev_fork, stream));
+    for (int i = 0; i < ss_ctx::kAux; ++i) CK(cudaStreamWaitEvent(c->s_aux[i], p->ev_fork, 0));
+    int rc = SS_OK;
+    for (size_t k = 0; k < n_chunks && rc == SS_OK; ++k) rc = chunk_enqueue(c, p->chunks[k], c->s_aux[k % ss_ctx::kAux], nullptr);
+    for (int i = 0; i < ss_ctx::kAux; ++i) {
+        CK(cudaEventRecord(p->ev_join[i], c->s_aux[i]));
+        CK(cudaStreamWaitEvent(stream, p->ev_join[i], 0));
+    }
+    return rc;
+}
+
+extern "C" int ss_plan_run(ss_plan* p, void* stream_) {
+    if (!p) return SS_ERR_INVALID;
+    ss_ctx* c = p->c;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(cudaSetDevice(c->device));
+    if (c->profiling) {
+        // per-kernel timing: chunks one after the other on the caller's stream, events around every launch
+        c->prof_chunk = 0;
+        k_delay<<<1, 1, 0, stream>>>(300000u);
+        CK(cudaGetLastError());
+        for (auto& L : p->chunks) {
+            ss_ctx::Prof pf;
+            CK(cudaEventCreate(&pf.e0)); CK(cudaEventCreate(&pf.e1)); CK(cudaEventCreate(&pf.e2));
+            pf.chunk = c->prof_chunk++;
+            int st = chunk_enqueue(c, L, stream, &pf);
+            c->prof.push_back(pf);
+            if (st) return st;
+        }
+        return SS_OK;
+    }
+    if (!p->exec && !p->graph_failed && !c->no_graph) {
+        const int64_t launches_before = c->launches;
+        cudaGraph_t g = nullptr;
+        bool ok = cudaStreamBeginCapture(p->s_cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            const int st = plan_enqueue(p, p->s_cap);
+            const cudaError_t e = cudaStreamEndCapture(p->s_cap, &g);
+            ok = st == SS_OK && e == cudaSuccess && g != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&p->exec, g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        c->launches = launches_before;                      // nothing ran while capturing
+        if (!ok) { p->exec = nullptr; p->graph_failed = true; (void)cudaGetLastError(); }
+    }
+    if (p->exec) {
+        CK(cudaGraphLaunch(p->exec, stream));
+        c->launches += p->launches_per_run;
+        return SS_OK;
+    }
+    return plan_enqueue(p, stream);
+}
+// 1: the plan runs as an instantiated CUDA graph, 0: not (yet), negative: error
+extern "C" int ss_plan_is_graph(const ss_plan* p) { return p ? (p->exec ? 1 : 0) : SS_ERR_INVALID; }
 
 // ----------------------------------------------------------------------------- host path
 static int check_traj_host(const ss_source& it) {

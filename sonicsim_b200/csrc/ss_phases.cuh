@@ -60,7 +60,9 @@ struct RItem {
     int p_lo, p_hi;        // transforms p = p_lo, p_lo + 2, ... <= p_hi   (static: 0, 0)
     int mode;
     int kparts;            // RIR partitions that reach back into the signal: min(K, n0 / 4096 + 1)
-    int pad_[5];
+    int b0;                // aligned blocking: first sample of the block's segment, bounds[p_lo] ...
+    double step;           // ... and 1 / (samples in that segment), so that k_render_fast's output stage loads no table
+    int pad_[2];
 };
 static_assert(sizeof(RItem) == 112, "RItem is copied as 7 x 16 B");
 
@@ -102,8 +104,8 @@ SS_HD void fill_items(const Source& s, RItem* items, int blk, const Block& bk, i
     it.mode = s.mode;
     const int reach = bk.start / kB + 1;
     it.kparts = reach < s.K ? reach : s.K;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) it.pad_[i] = 0;
+    it.b0 = 0; it.step = 0.0; it.pad_[0] = 0; it.pad_[1] = 0;
+    if (s.aligned) { it.b0 = s.bounds[bk.p_lo]; it.step = s.rstep[bk.p_lo]; }
     const int per = items_per_block(s);
     RItem* dst = items + s.counts[1] + (size_t)blk * per;
     if (s.mode == MODE_STATIC) {
@@ -443,6 +445,16 @@ SS_HD void render_phase3(int t, Regs32& R, const Tables& T) {
         R.a[sl] = cfms(R.a[sl], u[r], R.b[sl]);
     }
 }
+// the closing radix-2 alone (pass C already done by the caller)
+SS_HD void render_phase3_close(int t, Regs32& R, const Tables& T) {
+    float2 u[16];
+    final_twiddles<true>(dirw<true>(ldg_cached(T.tw + t)), u);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int sl = out16(r);
+        R.a[sl] = cfms(R.a[sl], u[r], R.b[sl]);
+    }
+}
 // hat functions of positions (p, p+1) at a sample that lies in segment sg with weight w:
 //   reference lerp (SonicSim_moving.py:94):  (1 - w) * conv[sg] + w * conv[sg + 1]
 SS_HD void hat_pair(int sg, float w, int p, float& fa, float& fb) {
@@ -529,6 +541,26 @@ SS_HD void render_epilogue(int t, const XDesc& d, const Regs32& R) {
                 if (first) row[n] = v; else red_add(row + n, v);
             }
         }
+    }
+}
+
+// Output stage of k_render_fast (aligned blocking: the block lies in segment p_lo, one transform per item): as the
+// single-segment branch above, with the segment's first sample and 1 / length taken from the work item itself.
+SS_HD void render_epilogue_item(int t, const RItem& it, const Regs32& R) {
+    const int nbase = it.n0 + t, n_end = it.n_end;
+    float* const row = it.row;
+    if (nbase >= n_end) return;
+    const double d0 = (double)(nbase - it.b0);
+    const double step = it.step;
+    float w[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) w[r] = (float)((d0 + 256.0 * r) * step);   // == np.linspace(0, 1, num, False)[i] as float32
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int n = nbase + 256 * r;
+        const float2 z = R.a[out16(r)];
+        const float v = lerp_terms(one_minus(w[r]), z.x, w[r], z.y);
+        if (n < n_end) row[n] = v;
     }
 }
 

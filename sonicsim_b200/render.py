@@ -106,29 +106,70 @@ class Renderer:
     def render_device(self, sources, outs, stream: T.Optional[int] = None):
         """`sources`: MovingSource / StaticSource whose fields are CUDA float32 / int32 tensors;
         `outs`: preallocated CUDA (C, N) tensors.  Asynchronous on `stream` (torch current stream)."""
-        self.plan_device(sources, outs).run(stream)
+        items, n, keep = self._device_items(sources, outs)
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.lib.ss_render_dev(self.ctx, items, n, ctypes.c_void_p(stream)))
 
     def plan_device(self, sources, outs) -> "DevicePlan":
         """Bind a batch of device-resident sources to its output tensors once; `plan.run()` then renders it with a
-        single C-ABI call (a generation loop overwrites the same tensors and calls run() again)."""
+        single C-ABI call - one CUDA graph launch (ss_plan_run; a generation loop overwrites the same tensors and
+        calls run() again).  Every tensor must be a contiguous CUDA tensor of this renderer's device: float32 dry
+        (N,), RIRs (P, C, L) / (C, L), outs[i] (C, N) for that source's own C and N; int32 bounds (P,)."""
+        return DevicePlan(self, *self._device_items(sources, outs))
+
+    def _device_items(self, sources, outs):
+        """Validated ss_source array of a device-resident batch: (items, n, objects to keep alive)."""
+        import torch
         n = len(sources)
+        if len(outs) != n:
+            raise ValueError("plan_device: %d sources but %d output tensors" % (n, len(outs)))
         items = (SsSource * n)()
         keep = [sources, outs]
+
+        def chk(t, name, i, dtype, shape=None):
+            if not isinstance(t, torch.Tensor) or not t.is_cuda:
+                raise ValueError("plan_device: %s of source %d must be a CUDA tensor" % (name, i))
+            if self.device is not None and t.device.index != self.device:
+                raise ValueError("plan_device: %s of source %d is on cuda:%s, the renderer on cuda:%d"
+                                 % (name, i, t.device.index, self.device))
+            if t.dtype != dtype:
+                raise ValueError("plan_device: %s of source %d must be %s, got %s" % (name, i, dtype, t.dtype))
+            if not t.is_contiguous():
+                raise ValueError("plan_device: %s of source %d must be contiguous" % (name, i))
+            if shape is not None and tuple(t.shape) != tuple(shape):
+                raise ValueError("plan_device: %s of source %d must have shape %s, got %s"
+                                 % (name, i, tuple(shape), tuple(t.shape)))
+
         for i, s in enumerate(sources):
+            chk(s.dry, "dry", i, torch.float32)
+            N = s.dry.numel()
             if isinstance(s, StaticSource):
+                chk(s.rir, "rir", i, torch.float32)
+                if s.rir.dim() != 2:
+                    raise ValueError("plan_device: rir of static source %d must be (C, L)" % i)
                 C, L = s.rir.shape
+                chk(outs[i], "out", i, torch.float32, (C, N))
                 items[i] = SsSource(x=s.dry.data_ptr(), rir=s.rir.data_ptr(), out=outs[i].data_ptr(),
-                                    N=s.dry.numel(), P=1, C=C, L=L, mode=_lib.SS_STATIC)
+                                    N=N, P=1, C=C, L=L, mode=_lib.SS_STATIC)
             else:
+                chk(s.rirs, "rirs", i, torch.float32)
+                if s.rirs.dim() != 3:
+                    raise ValueError("plan_device: rirs of moving source %d must be (P, C, L)" % i)
                 P, C, L = s.rirs.shape
+                chk(outs[i], "out", i, torch.float32, (C, N))
+                chk(s.bounds, "bounds", i, torch.int32, (P,))
                 bh = None
                 if s.bounds_host is not None:
                     bh = np.ascontiguousarray(s.bounds_host, dtype=np.int32)
+                    if bh.shape != (P,):
+                        raise ValueError("plan_device: bounds_host of source %d must have P entries" % i)
                     keep.append(bh)
                 items[i] = SsSource(x=s.dry.data_ptr(), rir=s.rirs.data_ptr(), out=outs[i].data_ptr(),
-                                    bounds=s.bounds.data_ptr(), N=s.dry.numel(), P=P, C=C, L=L,
+                                    bounds=s.bounds.data_ptr(), N=N, P=P, C=C, L=L,
                                     mode=_lib.SS_MOVING_BOUNDS, bounds_host=bh.ctypes.data if bh is not None else None)
-        return DevicePlan(self, items, n, keep)
+        return items, n, keep
 
     def launch_count(self) -> int:
         return int(self.lib.ss_launch_count(self.ctx))
@@ -150,17 +191,37 @@ class Renderer:
 
 
 class DevicePlan:
-    """A batch of device-resident sources bound to its output tensors (Renderer.plan_device)."""
+    """A batch of device-resident sources bound to its output tensors (Renderer.plan_device): an ss_plan of the C ABI -
+    descriptors, block tables and scratch resident on the device, the launches captured into a CUDA graph."""
 
     def __init__(self, renderer, items, n, keep):
         self.renderer, self.items, self.n, self._keep = renderer, items, n, keep
+        self._plan = ctypes.c_void_p()
+        if n > 0:
+            _lib.check(renderer.lib.ss_plan_create(renderer.ctx, items, n, ctypes.byref(self._plan)))
 
     def run(self, stream: T.Optional[int] = None):
         """Asynchronous on `stream` (default: torch's current stream)."""
+        if self.n == 0:
+            return
         if stream is None:
             import torch
             stream = torch.cuda.current_stream().cuda_stream
-        _lib.check(self.renderer.lib.ss_render_dev(self.renderer.ctx, self.items, self.n, ctypes.c_void_p(stream)))
+        _lib.check(self.renderer.lib.ss_plan_run(self._plan, ctypes.c_void_p(stream)))
+
+    def is_graph(self) -> bool:
+        return self.n > 0 and self.renderer.lib.ss_plan_is_graph(self._plan) == 1
+
+    def close(self):
+        if self._plan:
+            self.renderer.lib.ss_plan_destroy(self._plan)
+            self._plan = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class HostPlan:
@@ -250,6 +311,11 @@ def render_mixtures(utterances: T.Sequence[dict], device: T.Optional[int] = None
         S, M = len(u["speakers"]), len(u["noises"])
         N = int(np.asarray(u["speakers"][0][0]).shape[-1])
         C = int(np.asarray(u["speakers"][0][1]).shape[1])
+        for d, h, *_ in list(u["speakers"]) + list(u["noises"]):
+            hs = np.asarray(h).shape
+            if int(np.asarray(d).shape[-1]) != N or int(hs[-2]) != C:
+                raise ValueError("render_mixtures: every stem of an utterance must have the same (C, N); got N=%d C=%d "
+                                 "against N=%d C=%d" % (int(np.asarray(d).shape[-1]), int(hs[-2]), N, C))
         spk = torch.empty((S, C, N), dtype=torch.float32, device=dev)
         noi = torch.empty((M, C, N), dtype=torch.float32, device=dev)
         for i, (d, h, pos) in enumerate(u["speakers"]):

@@ -174,6 +174,61 @@ static void cta_render(const RItem* items, int n_items, int cta, int grid, const
     }
 }
 
+// One persistent k_render_fast CTA: the kernel's control flow with the split barriers collapsed (every phase runs for all
+// threads before the next starts) and the bulk copies / item prefetches done at the points where the kernel issues them.
+static void cta_render_fast(const RItem* items, int n_items, int cta, int grid, const Tables& T) {
+    std::vector<float2> smem(kPadF + kSpec);
+    std::vector<Regs32> R(kThreads);
+    float2* const fftbuf = smem.data();
+    float2* const sX = fftbuf;
+    float2* const sHp = fftbuf + kSpec;
+    float2* const sHq = fftbuf + kPadF;
+    const int n_k = (n_items - cta + grid - 1) / grid;
+    if (n_k <= 0) return;
+    const RItem* my_items = items + cta;
+    RItem s_item[3];
+    s_item[0] = my_items[0];
+    if (n_k > 1) s_item[1] = my_items[grid];
+    {
+        const float2* hp = s_item[0].H0 + (size_t)s_item[0].p_lo * s_item[0].pstride;
+        memcpy(sX, s_item[0].X, sizeof(float2) * kSpec);
+        memcpy(sHp, hp, sizeof(float2) * kSpec);
+        memcpy(sHq, hp + s_item[0].pstride, sizeof(float2) * kSpec);
+    }
+    XDesc unused; memset(&unused, 0, sizeof(unused)); unused.kparts = 1;
+    std::vector<float2> w(kThreads * 16);
+    for (int k = 0; k < n_k; ++k) {
+        for (int t = 0; t < kThreads; ++t) form_z<false, true>(t, sX, sHp, sHq, unused, R[t]);
+        for (int t = 0; t < kThreads; ++t) { fft16<true>(R[t].a); fft16<true>(R[t].b); }
+        if (k + 1 < n_k) {
+            const RItem& nx = s_item[(k + 1) % 3];
+            memcpy(sHq, nx.H0 + (size_t)(nx.p_lo + 1) * nx.pstride, sizeof(float2) * kSpec);
+        }
+        if (k + 2 < n_k) s_item[(k + 2) % 3] = my_items[(size_t)(k + 2) * grid];
+        for (int t = 0; t < kThreads; ++t) { passA_store(fftbuf, passA_jA(t), R[t].a); passA_store(fftbuf, passA_jB(t), R[t].b); }
+        for (int t = 0; t < kThreads; ++t) load2(t, fftbuf, R[t]);
+        for (int t = 0; t < kThreads; ++t) {
+            float2 (&wt)[16] = *reinterpret_cast<float2 (*)[16]>(&w[16 * t]);
+            tw_load<true, 16>(T.twB + (t & 15), wt);
+            fft16_w<true>(R[t].a, wt); fft16_w<true>(R[t].b, wt);
+        }
+        for (int t = 0; t < kThreads; ++t) { passB_store(fftbuf, t, R[t].a); passB_store(fftbuf, t + 256, R[t].b); }
+        for (int t = 0; t < kThreads; ++t) load2(t, fftbuf, R[t]);
+        if (k + 1 < n_k) {
+            const RItem& nx = s_item[(k + 1) % 3];
+            memcpy(sX, nx.X, sizeof(float2) * kSpec);
+            memcpy(sHp, nx.H0 + (size_t)nx.p_lo * nx.pstride, sizeof(float2) * kSpec);
+        }
+        for (int t = 0; t < kThreads; ++t) {
+            float2 (&wt)[16] = *reinterpret_cast<float2 (*)[16]>(&w[16 * t]);
+            tw_load<true, 256>(T.twC + t, wt);
+            fft16_w<true>(R[t].a, wt); fft16_w<true>(R[t].b, wt);
+            render_phase3_close(t, R[t], T);
+            render_epilogue_item(t, s_item[k % 3], R[t]);
+        }
+    }
+}
+
 extern "C" {
 
 // Emulate k_spectra + k_render for one source.  mode: 0 static, 1 bounds, 2 (idx, w).
@@ -198,7 +253,10 @@ int emu_render(const float* x, const float* rir, float* out, const int32_t* boun
     prepare_ranges(S, items.data());
     const int nr = counts[0] * items_per_block(S);
     const int grid = nr < 3 ? nr : 3;              // a few persistent CTAs, each looping over many items
-    for (int cta = 0; cta < grid; ++cta) cta_render(items.data(), nr, cta, grid, T, S.aligned != 0, S.K > 1);
+    for (int cta = 0; cta < grid; ++cta) {
+        if (S.aligned) cta_render_fast(items.data(), nr, cta, grid, T);
+        else cta_render(items.data(), nr, cta, grid, T, false, S.K > 1);
+    }
     return 0;
 }
 

@@ -18,7 +18,7 @@ def test_reference_arm_json_line():
         assert key in line, key
     assert line["impl"] == "reference" and line["metric"] == "rendered_audio_seconds_per_second"
     assert line["value"] > 0 and line["steps"] == 2 and line["vs_baseline"] is None
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
 
 

@@ -281,3 +281,61 @@ def test_host_plan_rerun_with_refilled_buffers():
         np.random.seed(10 + it)
         bounds[:] = render.trajectory_bounds(so.synth_path(rng, P), N)
         xs[:] = so.synth_dry(rng, N)
+
+
+def test_device_plan_is_one_graph_launch_and_matches_direct_launches():
+    """Renderer.plan_device -> ss_plan_*: descriptors + scratch resident, launches captured into a CUDA graph (several
+    chunks forked over the internal streams).  Must equal ss_render_dev bit for bit, pick up refilled buffers, and
+    reject tensors that would make the kernels write out of bounds."""
+    from sonicsim_b200 import render
+    rng = np.random.default_rng(321)
+    R = render.default_renderer()
+    R.set_chunk_bytes(8 << 20)                       # several chunks -> fork / join inside the graph
+    try:
+        dev, outs, host = [], [], []
+        for i in range(9):
+            N, C, P = int(rng.integers(20000, 60000)), int(rng.integers(1, 5)), int(rng.integers(2, 9))
+            L = int(rng.integers(100, 4096)) if i % 3 else int(rng.integers(4097, 7000))
+            x, h = so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L)
+            np.random.seed(40 + i)
+            b = render.trajectory_bounds(so.synth_path(rng, P), N)
+            host.append((x, h, b))
+            dev.append(render.MovingSource(torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda(), torch.from_numpy(b).cuda(),
+                                           b if i % 2 == 0 else None))
+            outs.append(torch.empty((C, N), device="cuda"))
+        xs, hs_ = so.synth_dry(rng, 30000), so.synth_rirs(rng, 1, 3, 700)[0]
+        dev.append(render.StaticSource(torch.from_numpy(xs).cuda(), torch.from_numpy(hs_).cuda()))
+        outs.append(torch.empty((3, 30000), device="cuda"))
+        direct = [torch.empty_like(o) for o in outs]
+        R.render_device(dev, direct)
+        plan = R.plan_device(dev, outs)
+        n0 = R.launch_count()
+        plan.run()
+        torch.cuda.synchronize()
+        assert plan.is_graph()
+        assert R.launch_count() > n0                  # the graph's kernels are counted
+        for o, d in zip(outs, direct):
+            assert torch.equal(o, d)
+        # refill one dry signal in place: the next run must see it
+        x0 = so.synth_dry(rng, host[0][0].shape[0])
+        dev[0].dry.copy_(torch.from_numpy(x0))
+        for o in outs:
+            o.zero_()
+        plan.run()
+        torch.cuda.synchronize()
+        one = R.render_host([render.MovingSource(x0, host[0][1], host[0][2])])[0]
+        assert np.array_equal(outs[0].cpu().numpy(), one)
+        for o, d in zip(outs[1:], direct[1:]):
+            assert torch.equal(o, d)
+        plan.close()
+        # validation of device tensors
+        with pytest.raises(ValueError):
+            R.plan_device([dev[0]], [torch.empty((outs[0].shape[0], outs[0].shape[1] - 1), device="cuda")])
+        with pytest.raises(ValueError):
+            R.plan_device([dev[0]], [outs[0].double()])
+        with pytest.raises(ValueError):
+            R.plan_device([render.MovingSource(dev[0].dry, dev[0].rirs.transpose(1, 2), dev[0].bounds)], [outs[0]])
+        with pytest.raises(ValueError):
+            R.plan_device([render.MovingSource(dev[0].dry.cpu(), dev[0].rirs, dev[0].bounds)], [outs[0]])
+    finally:
+        R.set_chunk_bytes(96 << 20)
