@@ -47,6 +47,15 @@ typedef enum {
     SS_MOVING_INDEXED = 2     /* `idx` (int32, N) and `w` (float32, N): interp_index / interp_weight */
 } ss_mode;
 
+/* per-source options (ss_source.flags) */
+typedef enum {
+    SS_RIR_NORMALIZE = 1      /* `rir` is the raw simulator output, clipped and stacked: divide every tap by the global
+                               * abs-max of the source's whole (P, C, L) tensor before convolving, i.e. the
+                               * `ir_output /= ir_output.abs().max()` of generate_rir_combination
+                               * (SonicSim_audio.py:391-398), fused into the spectra kernel's row loads (one reduction
+                               * kernel + an IEEE division per tap; same bits as normalising first) */
+} ss_source_flags;
+
 /* One (utterance, source) unit of work = one call of convolve_moving_receiver /
  * convolve_fixed_receiver in the reference.  Pointers are device pointers for ss_render_dev and
  * host pointers for ss_render_host. */
@@ -59,7 +68,7 @@ typedef struct {
     const float* w;           /* SS_MOVING_INDEXED: interp_weight (SonicSim_moving.py:43)            */
     int32_t N, P, C, L;
     int32_t mode;             /* ss_mode */
-    int32_t reserved;
+    int32_t flags;            /* ss_source_flags, 0 = none */
     const int32_t* bounds_host; /* ss_render_dev only, optional: HOST copy of `bounds` (P ints).  With it the block
                                  * table is built on the host and one small kernel launch per chunk is saved.     */
 } ss_source;
@@ -182,6 +191,24 @@ int ss_mix_host_ex(ss_ctx* ctx, const float* speakers, const float* noises, cons
  * zeros outside [0, T); x != y. */
 int ss_overlap_dev(ss_ctx* ctx, const float* x, float* y, int32_t rows, int64_t T, int64_t delay, void* stream);
 int ss_overlap_host(ss_ctx* ctx, const float* x, float* y, int32_t rows, int64_t T, int64_t delay);
+
+/* ---- dry-stream assembly: the arithmetic of SonicSim_audio.create_long_audio (SonicSim_audio.py:231-279) and
+ * create_background_audio (:281-340) once the host has drawn the clips and their places (`random` stream as in the
+ * reference): resampling with torchaudio.transforms.Resample's polyphase filter bank (:253-256), stereo -> mono mean
+ * (:311-312) and `long_audio[:, a:b] += clip[...]` (:268, :326, :332), one kernel, the stream stays in HBM. */
+typedef struct {
+    const float* src;         /* (channels, src_len) device: the decoded clip at its own sample rate            */
+    const float* kernel_t;    /* (taps, new_rate) device: Resample.kernel[:, 0, :] transposed; NULL = same rate  */
+    int64_t dst_start;        /* first sample of the stream written                                             */
+    int64_t src_start;        /* first sample of the (resampled, mono) clip used                                 */
+    int64_t count;            /* samples added                                                                   */
+    int32_t channels;         /* 1, or 2 (averaged after resampling)                                             */
+    int32_t src_len;
+    int32_t orig, new_rate;   /* sample rates divided by their gcd (Resample.orig_freq / gcd, new_freq / gcd)    */
+    int32_t width, taps;      /* Resample.width; taps = 2 * width + orig                                         */
+} ss_dry_clip;
+/* zero-fills out[0, total) and adds every clip; device pointers, asynchronous on `stream` */
+int ss_dry_assemble_dev(ss_ctx* ctx, const ss_dry_clip* clips, int n_clips, float* out, int64_t total, void* stream);
 
 /* Counters since ss_create / ss_reset_stats: kernels launched and device time is NOT measured
  * here (bench.py uses CUDA events); this is the launch count bench.py reports as gpu_launches. */

@@ -234,8 +234,43 @@ def golden_dry():
     print("dry_assembly.json", len(cases), "cases")
 
 
+def golden_rir_combine():
+    """f4: RIR post-processing - the reference's own lines, exec'd verbatim: clip_all (SonicSim_rir.py:24-41; the module
+    needs habitat_sim, so the function's source lines are exec'd) and the tail of generate_rir_combination
+    (SonicSim_audio.py:391-398: clip, stack, reshape, divide by the global abs-max)."""
+    import textwrap
+    import torch
+    rir_src = open("/root/reference/SonicSim-SonicSet/SonicSim_rir.py").read().splitlines()
+    aud_src = open("/root/reference/SonicSim-SonicSet/SonicSim_audio.py").read().splitlines()
+    assert rir_src[23].startswith("def clip_all") and rir_src[40].strip() == "return clipped_audio_list", (rir_src[23], rir_src[40])
+    assert aud_src[390].strip().startswith("ir_list = clip_all(ir_list)") and aud_src[397].strip().startswith("ir_output /="), \
+        (aud_src[390], aud_src[397])
+    ns = {"torch": torch}
+    exec("\n".join(rir_src[23:41]), ns)
+    body = textwrap.dedent("\n".join(aud_src[390:398]))
+    cases = {}
+    for k, (seed, P, C, L0) in enumerate([(81, 5, 2, 700), (82, 6, 3, 2100), (83, 3, 1, 33)]):
+        rng = np.random.default_rng(seed)
+        lens = [L0 + int(rng.integers(0, 40)) for _ in range(P)]
+        raw = [(so.synth_rirs(rng, 1, C, l)[0] * float(rng.uniform(0.2, 3.0))).astype(np.float32) for l in lens]
+        env = dict(ns)
+        env.update(ir_list=[torch.from_numpy(r.copy()) for r in raw], source_idx_list=list(range(P)), receiver_idx_list=[0])
+        exec(body, env)
+        out = env["ir_output"].numpy()
+        assert out.shape == (P, 1, C, min(lens)) and out.dtype == np.float32
+        pad = np.zeros((P, C, max(lens)), np.float32)
+        for i, r in enumerate(raw):
+            pad[i, :, :lens[i]] = r
+        cases[f"raw{k}"], cases[f"lens{k}"], cases[f"out{k}"] = pad, np.asarray(lens, np.int64), out
+    cases["n_cases"] = np.int64(3)
+    np.savez_compressed(os.path.join(OUT, "rir_combine.npz"), **cases)
+    print("rir_combine.npz", 3, "cases")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "mix_noisy":
+    if len(sys.argv) > 1 and sys.argv[1] == "rir_combine":
+        golden_rir_combine()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mix_noisy":
         golden_mix_noisy()
     elif len(sys.argv) > 1 and sys.argv[1] == "dry":
         golden_dry()
@@ -243,3 +278,4 @@ if __name__ == "__main__":
         main()
         golden_mix_noisy()
         golden_dry()
+        golden_rir_combine()

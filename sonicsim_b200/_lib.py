@@ -12,13 +12,14 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libsonicsim_b200.so")
-SOURCES = ["ss_kernels.cu", "ss_loudness.cu", "ss_mix.cu"]
+SOURCES = ["ss_kernels.cu", "ss_loudness.cu", "ss_mix.cu", "ss_dry.cu"]
 HEADERS = ["ss_core.cuh", "ss_phases.cuh", "ss_loud.cuh", "ss_internal.h", os.path.join("..", "..", "include", "sonicsim_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
 SS_OK, SS_ERR_INVALID, SS_ERR_INDEX, SS_ERR_CUDA, SS_ERR_NOMEM, SS_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 SS_STATIC, SS_MOVING_BOUNDS, SS_MOVING_INDEXED = 0, 1, 2
+SS_RIR_NORMALIZE = 1
 
 
 class SsLoudItem(ctypes.Structure):
@@ -38,6 +39,14 @@ class SsMixItem(ctypes.Structure):
                 ("noise_delay", ctypes.c_int32)]
 
 
+class SsDryClip(ctypes.Structure):
+    """`ss_dry_clip` of include/sonicsim_b200.h."""
+    _fields_ = [("src", ctypes.c_void_p), ("kernel_t", ctypes.c_void_p), ("dst_start", ctypes.c_int64),
+                ("src_start", ctypes.c_int64), ("count", ctypes.c_int64), ("channels", ctypes.c_int32),
+                ("src_len", ctypes.c_int32), ("orig", ctypes.c_int32), ("new_rate", ctypes.c_int32),
+                ("width", ctypes.c_int32), ("taps", ctypes.c_int32)]
+
+
 class SsPostLufs(ctypes.Structure):
     """`ss_post_lufs` of include/sonicsim_b200.h."""
     _fields_ = [("brk", ctypes.c_void_p), ("blk_lo", ctypes.c_void_p), ("blk_hi", ctypes.c_void_p),
@@ -50,7 +59,7 @@ class SsSource(ctypes.Structure):
     _fields_ = [("x", ctypes.c_void_p), ("rir", ctypes.c_void_p), ("out", ctypes.c_void_p),
                 ("bounds", ctypes.c_void_p), ("idx", ctypes.c_void_p), ("w", ctypes.c_void_p),
                 ("N", ctypes.c_int32), ("P", ctypes.c_int32), ("C", ctypes.c_int32), ("L", ctypes.c_int32),
-                ("mode", ctypes.c_int32), ("reserved", ctypes.c_int32), ("bounds_host", ctypes.c_void_p)]
+                ("mode", ctypes.c_int32), ("flags", ctypes.c_int32), ("bounds_host", ctypes.c_void_p)]
 
 
 def _stale():
@@ -127,6 +136,7 @@ def load():
         lib.ss_mix_host_ex.argtypes = [vp, vp, vp, vp, ctypes.c_float, vp, vp, i32, i32, i64, i32]
         lib.ss_overlap_dev.argtypes = [vp, vp, vp, i32, i64, i64, vp]
         lib.ss_overlap_host.argtypes = [vp, vp, vp, i32, i64, i64]
+        lib.ss_dry_assemble_dev.argtypes = [vp, ctypes.POINTER(SsDryClip), ctypes.c_int, vp, i64, vp]
         lib.ss_debug_plan.argtypes = [ctypes.POINTER(SsSource), vp, i32, ctypes.POINTER(i32)]
         lib.ss_launch_count.argtypes = [vp]
         lib.ss_launch_count.restype = i64
@@ -145,7 +155,7 @@ def load():
 EXPORTS = ["ss_version", "ss_strerror", "ss_last_cuda_error", "ss_create", "ss_destroy",
            "ss_set_chunk_bytes", "ss_render_dev", "ss_plan_create", "ss_plan_run", "ss_plan_is_graph", "ss_plan_destroy", "ss_render_host", "ss_render_host_ex", "ss_convolve_fixed_receiver",
            "ss_convolve_moving_receiver", "ss_loudness_dev", "ss_lufs_norm_host", "ss_mix_scratch_doubles", "ss_mix_dev", "ss_mix_host",
-           "ss_mix_host_ex", "ss_overlap_dev", "ss_overlap_host", "ss_debug_plan", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
+           "ss_mix_host_ex", "ss_overlap_dev", "ss_overlap_host", "ss_dry_assemble_dev", "ss_debug_plan", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
            "ss_host_free"]
 
 

@@ -93,6 +93,31 @@ k_blocks(const Source* __restrict__ srcs, int n_src, int* __restrict__ total_ite
     }
 }
 
+// ----------------------------------------------------------------------------- k_rir_absmax
+// SS_RIR_NORMALIZE: partial maxima of |h| over a source's whole (P, C, L) tensor, kNormParts CTAs per source, each
+// writing its own slot (no atomics, nothing to reset between runs); k_prepare's RIR rows take the maximum of the
+// slots and divide their taps by it - generate_rir_combination's `ir_output /= ir_output.abs().max()`
+// (SonicSim_audio.py:398) without a separate pass over the RIRs.
+__global__ void __launch_bounds__(256)
+k_rir_absmax(const Source* __restrict__ srcs) {
+    const Source& S = srcs[blockIdx.x / kNormParts];
+    if (!S.norm_part) return;
+    const int part = blockIdx.x % kNormParts;
+    const size_t total = (size_t)S.P * S.C * S.L;
+    float m = 0.f;
+    for (size_t i = (size_t)part * blockDim.x + threadIdx.x; i < total; i += (size_t)kNormParts * blockDim.x)
+        m = fmaxf(m, fabsf(S.rir[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float s_m[8];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, s_m[w]);
+        const_cast<float*>(S.norm_part)[part] = m;
+    }
+}
+
 // ----------------------------------------------------------------------------- k_prepare
 // CTA kinds, flattened per source through `prefix`:
 //   [0, nh)            two RIR-partition rows  -> two half spectra (one complex FFT)
@@ -716,6 +741,7 @@ static int validate_item(const ss_source& it) {
     // 32-bit sample / table indices inside the kernels: leave one FFT of headroom below 2^31
     if (it.N > 0x7fffffff - 2 * kF) return SS_ERR_UNSUPPORTED;
     if ((int64_t)it.P * it.C * ((it.L + kB - 1) / kB) > (int64_t)1 << 28) return SS_ERR_UNSUPPORTED;
+    if (it.flags & ~SS_RIR_NORMALIZE) return SS_ERR_INVALID;
     if (it.mode == SS_STATIC) { if (it.P != 1) return SS_ERR_INVALID; }
     else if (it.mode == SS_MOVING_BOUNDS) { if (it.P < 2 || !it.bounds) return SS_ERR_INVALID; }
     else if (it.mode == SS_MOVING_INDEXED) { if (it.P < 2 || !it.idx || !it.w) return SS_ERR_INVALID; }
@@ -756,7 +782,8 @@ static Shape shape_of(const ss_source& it) {
 static size_t spectra_bytes(const ss_source& it) {
     const Shape sh = shape_of(it);
     return ((size_t)it.P * it.C * sh.K + sh.nblk_max) * kSpec * sizeof(float2) + (size_t)sh.max_items * sizeof(RItem) +
-           align_up(sizeof(Block) * (size_t)sh.nblk_max, 256) + align_up(sizeof(double) * (size_t)it.P, 256) + 256;
+           align_up(sizeof(Block) * (size_t)sh.nblk_max, 256) + align_up(sizeof(double) * (size_t)it.P, 256) + 256 +
+           ((it.flags & SS_RIR_NORMALIZE) ? 256 : 0);
 }
 
 // Host-side twin of k_blocks for one source whose trajectory bounds are visible on the host.
@@ -808,7 +835,7 @@ extern "C" int ss_debug_plan(const ss_source* item, int32_t* blocks_out, int32_t
 // Everything the launches need besides the descriptor block in device memory.
 struct ChunkLaunch {
     int n = 0, ps = 0, grid_r = 0, n_known = -1;
-    bool host_tables = true, any_long = false, all_aligned = true;
+    bool host_tables = true, any_long = false, all_aligned = true, any_norm = false;
     const Source* ds = nullptr; const int* dps = nullptr; RItem* d_items = nullptr; int* d_total = nullptr;
     PrepParams pp;
 };
@@ -846,7 +873,7 @@ static void chunk_describe(const ss_source* items, int first, int last, char* hb
     int* hps = (int*)(hbase + off_ps);
     int ps = 0, pr = 0, total_items = 0;
     size_t tab_off = off_tot + 16;
-    bool any_long = false, all_aligned = true;
+    bool any_long = false, all_aligned = true, any_norm = false;
     for (int i = 0; i < n; ++i) {
         const ss_source& it = items[first + i];
         const Shape sh = shape_of(it);
@@ -860,6 +887,7 @@ static void chunk_describe(const ss_source* items, int first, int last, char* hb
         s.K = sh.K; s.nb = sh.nb; s.mode = it.mode; s.aligned = sh.aligned; s.nblk_max = sh.nblk_max;
         s.hspec = (float2*)scratch; scratch += (size_t)s.P * s.C * s.K * kSpec * sizeof(float2);
         s.xspec = (float2*)scratch; scratch += (size_t)s.nblk_max * kSpec * sizeof(float2);
+        if (it.flags & SS_RIR_NORMALIZE) { s.norm_part = (const float*)scratch; scratch += 256; any_norm = true; }
         if (host_tables) {
             // tables live in the descriptor block itself: filled here, copied with it
             Block* hb_blocks = (Block*)(hbase + tab_off);
@@ -888,6 +916,7 @@ static void chunk_describe(const ss_source* items, int first, int last, char* hb
     L->d_total = host_tables ? (int*)(dbase + off_tot) : (int*)scratch;
     if (host_tables) { *(int*)(hbase + off_tot) = total_items; pr = total_items; }
     L->n = n; L->ps = ps; L->host_tables = host_tables; L->any_long = any_long; L->all_aligned = all_aligned;
+    L->any_norm = any_norm;
     L->n_known = host_tables ? total_items : -1;
     L->grid_r = pr < sm_count * SS_RENDER_MINB ? pr : sm_count * SS_RENDER_MINB;
     L->ds = (const Source*)dbase;
@@ -903,6 +932,11 @@ static int chunk_enqueue(ss_ctx* c, const ChunkLaunch& L, cudaStream_t stream, s
     if (pf) CK(cudaEventRecord(pf->e0, stream));
     if (!L.host_tables) {
         k_blocks<<<1, 256, 0, stream>>>(L.ds, L.n, L.d_total);
+        CK(cudaGetLastError());
+        c->launches += 1;
+    }
+    if (L.any_norm) {
+        k_rir_absmax<<<L.n * kNormParts, 256, 0, stream>>>(L.ds);
         CK(cudaGetLastError());
         c->launches += 1;
     }
@@ -1084,7 +1118,7 @@ static int plan_build(ss_plan* p, const ss_source* items, int n_items) {
     for (size_t k = 0; k < n_chunks; ++k) {
         chunk_describe(items, cuts[k], cuts[k + 1], host.data() + off[k], p->d_desc + off[k],
                        p->d_scratch[n_chunks < 2 ? 0 : k % ss_ctx::kAux], c->sm_count, &p->chunks[k]);
-        p->launches_per_run += p->chunks[k].host_tables ? 2 : 3;
+        p->launches_per_run += (p->chunks[k].host_tables ? 2 : 3) + (p->chunks[k].any_norm ? 1 : 0);
     }
     CK(cudaMemcpy(p->d_desc, host.data(), off[n_chunks], cudaMemcpyHostToDevice));
     return SS_OK;

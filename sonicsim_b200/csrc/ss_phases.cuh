@@ -35,14 +35,16 @@ struct Source {
     Block* blocks;         // scratch: nblk_max blocks (k_blocks)
     double* rstep;         // scratch: 1 / (samples in segment s), s < P - 1 (mode 1)
     int* counts;           // scratch: [0] = blocks in use, [1] = index of this source's first render item
+    const float* norm_part;// scratch: kNormParts partial abs-maxima of the RIR tensor (k_rir_absmax), or null: taps used as given
     int N, P, C, L;
     int K;                 // RIR partitions = ceil(L / kB)
     int nb;                // ceil(N / kB)
     int mode;              // 0 static, 1 moving (bounds), 2 moving (idx, w)
     int aligned;           // 1: blocks aligned to the trajectory segments (mode 1 and K == 1)
     int nblk_max;          // table size: nb (grid) or nb + P - 1 (aligned)
-    int pad_[3];
+    int pad_[1];
 };
+constexpr int kNormParts = 32;     // CTAs (partial maxima) per normalised source in k_rir_absmax
 
 // One unit of k_render work: one block of channel c (static: channels c, c+1), written by k_prepare
 // so that k_render never searches trajectories, prefix tables or the Source array.
@@ -165,22 +167,31 @@ struct Row {
     float2* dst;           // null -> row absent (odd count / unused block slot)
     int nlo, nspan;        // nspan = nhi - nlo (0: empty)
     float scale;
+    float div;             // 0: samples as loaded; else every sample is divided by it first (SS_RIR_NORMALIZE)
 };
 SS_HD Row make_row(const float* base, float2* dst, int g0, int len, int ncap, float scale) {
     Row r;
-    r.dst = dst; r.scale = scale;
+    r.dst = dst; r.scale = scale; r.div = 0.f;
     int nlo = g0 < 0 ? -g0 : 0;
     int nhi = len - g0 < ncap ? len - g0 : ncap;
     r.nlo = nlo; r.nspan = nhi > nlo ? nhi - nlo : 0;
     r.src = base + g0;
     return r;
 }
-SS_HD Row no_row() { Row r; r.src = nullptr; r.dst = nullptr; r.nlo = 0; r.nspan = 0; r.scale = 0.f; return r; }
+SS_HD Row no_row() { Row r; r.src = nullptr; r.dst = nullptr; r.nlo = 0; r.nspan = 0; r.scale = 0.f; r.div = 0.f; return r; }
 
+// global abs-max of a normalised source's RIR tensor from k_rir_absmax's partial maxima
+SS_HD float rir_absmax(const Source& s) {
+    float m = 0.f;
+    for (int i = 0; i < kNormParts; ++i) { const float v = s.norm_part[i]; m = v > m ? v : m; }
+    return m;
+}
 SS_HD Row make_row_h(const Source& s, int row) {
     if (row >= s.P * s.C * s.K) return no_row();
     int part = row % s.K, pc = row / s.K;
-    return make_row(s.rir + (size_t)pc * s.L, s.hspec + (size_t)row * kSpec, part * kB, s.L, kB, 1.0f / (float)kF);
+    Row r = make_row(s.rir + (size_t)pc * s.L, s.hspec + (size_t)row * kSpec, part * kB, s.L, kB, 1.0f / (float)kF);
+    if (s.norm_part) r.div = rir_absmax(s);
+    return r;
 }
 SS_HD Row make_row_x(const Source& s, int blk) {
     if (blk >= s.nblk_max) return no_row();
@@ -190,6 +201,14 @@ SS_HD Row make_row_x(const Source& s, int blk) {
 }
 SS_HD float row_at(const Row& r, int n) {
     return ((unsigned)(n - r.nlo) < (unsigned)r.nspan) ? r.src[n] : 0.f;
+}
+// IEEE single-precision division, what `ir_output /= ir_output.abs().max()` does per element (SonicSim_audio.py:398)
+SS_HD float div_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
 }
 
 struct Regs32 { float2 a[16]; float2 b[16]; };
@@ -202,6 +221,14 @@ SS_HD void spectra_phase1(int t, const Row& ra, const Row& rb, float2* s) {
     for (int r = 0; r < 16; ++r) {
         R.a[r] = make_float2(row_at(ra, t + 512 * r), row_at(rb, t + 512 * r));
         R.b[r] = make_float2(row_at(ra, t + 256 + 512 * r), row_at(rb, t + 256 + 512 * r));
+    }
+    if (ra.div != 0.f || rb.div != 0.f) {            // CTA-uniform: rows of a source whose RIRs are normalised on the fly
+        const float da = ra.div != 0.f ? ra.div : 1.f, db = rb.div != 0.f ? rb.div : 1.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            R.a[r] = make_float2(div_rn(R.a[r].x, da), div_rn(R.a[r].y, db));
+            R.b[r] = make_float2(div_rn(R.b[r].x, da), div_rn(R.b[r].y, db));
+        }
     }
     fft16<false>(R.a); passA_store(s, t, R.a);
     fft16<false>(R.b); passA_store(s, t + 256, R.b);

@@ -36,6 +36,15 @@ def combine_rirs(ir_list, num_sources: int, num_receivers: int = 1) -> np.ndarra
     return out.astype(np.float32)
 
 
+def stack_rirs(ir_list, num_sources: int, num_receivers: int = 1) -> np.ndarray:
+    """The clip + stack half of SonicSim_audio.py:391-397 WITHOUT the normalisation: pass the result to the renderer
+    with `normalize_rirs=True` (ss_source.flags = SS_RIR_NORMALIZE) and the division by the global abs-max (:398) is
+    done on the device while the RIRs are transformed (k_rir_absmax + k_prepare) - same bits as combine_rirs."""
+    irs = [np.asarray(a.detach().cpu().numpy() if hasattr(a, "detach") else a, dtype=np.float32) for a in ir_list]
+    irs = clip_all(irs)
+    return np.ascontiguousarray(np.stack(irs).reshape(num_sources, num_receivers, len(irs[0]), -1))
+
+
 def load_rir_dump(path: str) -> T.List[np.ndarray]:
     """`torch.save(ir_outputs, ...)` of SonicSet.py:68 -> list of (P, C, L) float32 arrays (receiver axis squeezed,
     as interpolate_moving_audio does at SonicSim_moving.py:122)."""

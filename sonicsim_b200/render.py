@@ -25,12 +25,15 @@ class MovingSource(T.NamedTuple):
     rirs: T.Any
     bounds: T.Any
     bounds_host: T.Any = None
+    normalize_rirs: bool = False      # rirs = raw simulator output (formats.stack_rirs): divide by their global
+                                      # abs-max on the device like generate_rir_combination (SonicSim_audio.py:398)
 
 
 class StaticSource(T.NamedTuple):
     """One static source: dry (N,), RIR (C, L)."""
     dry: T.Any
     rir: T.Any
+    normalize_rirs: bool = False
 
 
 class Renderer:
@@ -74,7 +77,7 @@ class Renderer:
                 raise ValueError("out[%d] must be C-contiguous float32 of shape (C, N)" % i)
             items[i] = SsSource(x=x.ctypes.data, rir=h.ctypes.data, out=out.ctypes.data,
                                 bounds=bounds.ctypes.data if bounds is not None else None,
-                                N=N, P=P, C=C, L=L, mode=mode)
+                                N=N, P=P, C=C, L=L, mode=mode, flags=_lib.SS_RIR_NORMALIZE if s.normalize_rirs else 0)
             keep.append((x, h, bounds, out))
             results.append(out)
             if post is not None and lufs_targets[i] is not None:
@@ -152,7 +155,8 @@ class Renderer:
                 C, L = s.rir.shape
                 chk(outs[i], "out", i, torch.float32, (C, N))
                 items[i] = SsSource(x=s.dry.data_ptr(), rir=s.rir.data_ptr(), out=outs[i].data_ptr(),
-                                    N=N, P=1, C=C, L=L, mode=_lib.SS_STATIC)
+                                    N=N, P=1, C=C, L=L, mode=_lib.SS_STATIC,
+                                    flags=_lib.SS_RIR_NORMALIZE if s.normalize_rirs else 0)
             else:
                 chk(s.rirs, "rirs", i, torch.float32)
                 if s.rirs.dim() != 3:
@@ -168,7 +172,8 @@ class Renderer:
                     keep.append(bh)
                 items[i] = SsSource(x=s.dry.data_ptr(), rir=s.rirs.data_ptr(), out=outs[i].data_ptr(),
                                     bounds=s.bounds.data_ptr(), N=N, P=P, C=C, L=L,
-                                    mode=_lib.SS_MOVING_BOUNDS, bounds_host=bh.ctypes.data if bh is not None else None)
+                                    mode=_lib.SS_MOVING_BOUNDS, bounds_host=bh.ctypes.data if bh is not None else None,
+                                    flags=_lib.SS_RIR_NORMALIZE if s.normalize_rirs else 0)
         return items, n, keep
 
     def launch_count(self) -> int:

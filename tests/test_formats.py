@@ -67,3 +67,14 @@ def test_rir_dump_roundtrip_and_scene_writer(tmp_path):
     assert np.array_equal(back, stems[4])
     js = json.load(open(tmp_path / "scene" / "json_data.json"))
     assert sorted(js) == ["music", "noise", "source1", "source2", "source3"] and js["source2"]["words"] == ["HI"]
+
+
+def test_rir_postprocessing_against_golden_of_the_reference_lines(golden):
+    """combine_rirs / stack_rirs vs the golden written by exec'ing SonicSim_rir.py:24-41 + SonicSim_audio.py:391-398."""
+    g = golden("rir_combine")
+    for k in range(int(g["n_cases"])):
+        raw = [g[f"raw{k}"][i, :, :l] for i, l in enumerate(g[f"lens{k}"])]
+        out = g[f"out{k}"]
+        assert np.array_equal(formats.combine_rirs(raw, len(raw), 1), out)
+        st = formats.stack_rirs(raw, len(raw), 1)
+        assert st.shape == out.shape and np.array_equal(st / np.abs(st).max(), out)

@@ -75,7 +75,7 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
     pairs = {"ss_source": _lib.SsSource, "ss_loud_item": _lib.SsLoudItem, "ss_post_lufs": _lib.SsPostLufs,
-             "ss_mix_item": _lib.SsMixItem}
+             "ss_mix_item": _lib.SsMixItem, "ss_dry_clip": _lib.SsDryClip}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sonicsim_b200.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
