@@ -247,16 +247,37 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = time.perf_counter() - t_e0
     barrier()
     t_e1 = time.perf_counter()
+    # ---- copy-only floor of the e2e arm: the same bytes in both directions over PCIe, nothing else, on every rank at
+    # the same time (at N >= 4 the GPUs share PCIe switches / host memory and the floor itself rises)
+    n_floor = max(2, min(K * I, 12))
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def copy_pass():
+        with torch.cuda.stream(s_in):
+            for (hx, hh, _), ds in zip(h_items, d_srcs):
+                ds.dry.copy_(hx, non_blocking=True)
+                ds.rirs.copy_(hh, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for ho, do in zip(h_outs_t, d_outs):
+                ho.copy_(do, non_blocking=True)
+    copy_pass()
+    barrier()
+    t_f0 = time.perf_counter()
+    for _ in range(n_floor):
+        copy_pass()
+    torch.cuda.synchronize()
+    floor_s = (time.perf_counter() - t_f0) / n_floor
+    barrier()
     sampler.stop()
     # the device arm and the host arm must agree bit for bit (same kernels)
     same = bool(np.array_equal(h_outs[0], d_outs[0].cpu().numpy()))
     checksum = float(np.abs(h_outs[-1]).sum())          # the D2H'd result is really read
 
     # ---- max over ranks (device time), counters all-gather (the path's only collective)
-    tt = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=dev)
+    tt = torch.tensor([dev_s, e2e_s, floor_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_max, e2e_max = float(tt[0]), float(tt[1])
+    dev_max, e2e_max, floor_max = float(tt[0]), float(tt[1]), float(tt[2])
     counters = shard.gather_counters(step_audio * K, dev_s, step_alg * K, device=dev)
     issue_all = shard.gather_counters(t_issue, e2e_s, 0.0, device=dev)
     total_audio = float(counters[:, 0].sum())
@@ -320,7 +341,12 @@ def run_ours(args, rank, local_rank, world):
                        "per_rank_e2e_ms_per_step": [round(1e3 * float(t) / K, 3) for t in issue_all[:, 1]]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_b), "d2h_bytes_per_step": int(out_b),
-                    "ms_per_step": 1e3 * e2e_max / K, "api": "sonicsim_b200.render.Renderer.plan_host(...).run() -> ss_render_host",
+                    "ms_per_step": 1e3 * e2e_max / K, "ms_per_pass": 1e3 * e2e_max / K / I,
+                    "copy_floor_ms_per_pass": 1e3 * floor_max,
+                    "frac_of_copy_floor": floor_max / (e2e_max / K / I),
+                    "copy_floor_note": "pinned H2D of a pass's inputs and D2H of its outputs on two streams, no kernels, all "
+                                       "ranks at once (max over ranks); the e2e arm cannot be faster than this on this box",
+                    "api": "sonicsim_b200.render.Renderer.plan_host(...).run() -> ss_render_host",
                     "bit_identical_to_device_arm": same, "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -125,13 +125,14 @@ int ss_convolve_moving_receiver(ss_ctx* ctx, const float* source_audio, const fl
  * bounds are computed by the caller exactly as pyloudnorm does (Python float expressions
  * truncated with int()), and passed as `brk` = the sorted distinct bounds (n_e + 1 values) plus,
  * per gating block j, the range [blk_lo[j], blk_hi[j]) of elementary intervals it covers. */
+#define SS_LOUD_SCRATCH_DOUBLES 16
 typedef struct {
     const float* data;        /* element (n, c) at data[n * stride_n + c * stride_c]                   */
     float* out;               /* N*C contiguous floats = gain * data (may alias data); NULL = measure  */
     const int32_t* brk;       /* n_e + 1                                                               */
     const int32_t* blk_lo;    /* n_blocks                                                              */
     const int32_t* blk_hi;    /* n_blocks                                                              */
-    double* scratch;          /* C * n_e doubles                                                       */
+    double* scratch;          /* SS_LOUD_SCRATCH_DOUBLES * C * n_e doubles                             */
     double* result;           /* 2 doubles: integrated loudness (LUFS, may be -inf), linear gain       */
     int64_t stride_n, stride_c;
     int32_t N, C, n_e, n_blocks;

@@ -48,9 +48,24 @@ def _render_one(item: SsSource, keepalive):
     _lib.check(st)
 
 
+def _np_dtype(a):
+    """dtype NumPy would see for `a` (torch tensors included), for the output-dtype rule of the reference's NumPy code."""
+    if hasattr(a, "detach"):
+        return np.dtype(str(a.dtype).replace("torch.", ""))
+    return np.asarray(a).dtype
+
+
+def _out_dtype(*arrays):
+    """The reference runs scipy / NumPy on whatever it is given, so float64 in means float64 out.  The CUDA path
+    computes in float32 (the SonicSet pipeline is float32 end to end); a float64 caller gets the float32
+    result widened to float64 - same dtype as the reference, float32 accuracy."""
+    dt = np.result_type(np.float32, *[d for d in map(_np_dtype, arrays) if d.kind in "fc"])
+    return np.dtype(np.float64) if dt == np.float64 else np.dtype(np.float32)
+
+
 def convolve_fixed_receiver(source_audio, rirs) -> np.ndarray:
     """SonicSim_moving.py:47-61: `fftconvolve(x.reshape(1,-1), rirs, 'full')[:, :N]` -> (C, N)."""
-    in_dtype = np.result_type(np.asarray(source_audio).dtype if not hasattr(source_audio, "detach") else np.float32, np.float32)
+    out_dtype = _out_dtype(source_audio, rirs)
     x = _as_f32(source_audio).reshape(-1)
     h = _as_f32(rirs)
     if h.ndim != 2:
@@ -59,14 +74,15 @@ def convolve_fixed_receiver(source_audio, rirs) -> np.ndarray:
     N = x.shape[0]
     out = np.empty((C, N), dtype=np.float32)
     if N == 0:
-        return out
+        return out.astype(out_dtype, copy=False)
     it = SsSource(x=x.ctypes.data, rir=h.ctypes.data, out=out.ctypes.data, N=N, P=1, C=C, L=L, mode=_lib.SS_STATIC)
     _render_one(it, (x, h, out))
-    return out if in_dtype == np.float32 else out.astype(in_dtype)
+    return out.astype(out_dtype, copy=False)
 
 
 def convolve_moving_receiver(source_audio: np.ndarray, rirs: np.ndarray, interp_index, interp_weight) -> np.ndarray:
     """SonicSim_moving.py:63-96: (1 - w) * conv[idx] + w * conv[idx + 1] per sample -> (C, N)."""
+    out_dtype = _out_dtype(source_audio, rirs, interp_weight)
     x = _as_f32(source_audio)
     h = _as_f32(rirs)
     if x.ndim != 1 or h.ndim != 3:
@@ -74,22 +90,34 @@ def convolve_moving_receiver(source_audio: np.ndarray, rirs: np.ndarray, interp_
     P, C, L = h.shape
     N = x.shape[0]
     idx = np.asarray(interp_index)
+    if idx.dtype.kind not in "iu":                 # NumPy's own rule for the fancy index at :89
+        raise IndexError("arrays used as indices must be of integer (or boolean) type")
     w = np.ascontiguousarray(interp_weight, dtype=np.float32)
     if idx.shape != (N,) or w.shape != (N,):
         raise IndexError("interp_index / interp_weight must have shape (audio_len,)")
     out = np.empty((C, N), dtype=np.float32)
     if N == 0:
-        return out
-    # numpy fancy indexing semantics of :89-90: negative indices wrap, anything else out of range raises
-    if idx.min() < -P or idx.max() + 1 >= P or (idx.min() < 0 and (idx + 1).max() >= P):
-        raise IndexError("index %d is out of bounds for axis 0 with size %d" % (int(idx.max()) + 1, P))
-    if idx.min() < 0:
-        raise IndexError("negative interp_index is not supported by the CUDA path")
+        return out.astype(out_dtype, copy=False)
+    # NumPy fancy indexing of :89-90: `conv[idx]` and `conv[idx + 1]` each accept [-P, P); negative values wrap.
+    lo, hi = int(idx.min()), int(idx.max())
+    if lo < -P or hi + 1 >= P:
+        bad = lo if lo < -P else hi + 1
+        raise IndexError("index %d is out of bounds for axis 0 with size %d" % (bad, P))
+    if lo < 0:
+        # idx in [-P, -2] names the pair (idx + P, idx + P + 1); idx == -1 the pair (P - 1, 0): give the kernel a
+        # (P + 1)-th position that repeats position 0 so that every pair is (p, p + 1) again
+        idx = idx.astype(np.int64)
+        if (idx == -1).any():
+            h = np.ascontiguousarray(np.concatenate([h, h[:1]], axis=0))
+            P += 1
+            idx = np.where(idx < 0, idx + (P - 1), idx)
+        else:
+            idx = np.where(idx < 0, idx + P, idx)
     idx32 = np.ascontiguousarray(idx, dtype=np.int32)
     it = SsSource(x=x.ctypes.data, rir=h.ctypes.data, out=out.ctypes.data, idx=idx32.ctypes.data,
                   w=w.ctypes.data, N=N, P=P, C=C, L=L, mode=_lib.SS_MOVING_INDEXED)
     _render_one(it, (x, h, out, idx32, w))
-    return out
+    return out.astype(out_dtype, copy=False)
 
 
 def bounds_from_counts(samples_per_interval) -> np.ndarray:
@@ -112,8 +140,16 @@ def interpolate_moving_audio(source1_audio, ir1_list, receiver_position):
     h = _as_f32(ir1_list).squeeze(1)                                             # :122
     h = np.ascontiguousarray(h)
     P, C, L = h.shape
-    if bounds.shape[0] != P:
-        raise IndexError("number of receiver positions (%d) != number of RIRs (%d)" % (bounds.shape[0], P))
+    if bounds.shape[0] <= P:
+        # more RIRs than waypoints: interp_index never reaches the extra ones (the reference just ignores them)
+        P = bounds.shape[0]
+        h = np.ascontiguousarray(h[:P])
+    else:
+        # fewer RIRs than waypoints: the reference raises IndexError as soon as a sample needs position >= P
+        used = np.nonzero(np.diff(bounds))[0]
+        if used.size and used[-1] + 1 >= P:
+            raise IndexError("index %d is out of bounds for axis 0 with size %d" % (int(used[-1]) + 1, P))
+        bounds = np.ascontiguousarray(bounds[:P])
     out = np.empty((C, audio_len), dtype=np.float32)
     it = SsSource(x=x.ctypes.data, rir=h.ctypes.data, out=out.ctypes.data, bounds=bounds.ctypes.data,
                   N=audio_len, P=P, C=C, L=L, mode=_lib.SS_MOVING_BOUNDS)

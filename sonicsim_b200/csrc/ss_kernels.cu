@@ -1263,7 +1263,7 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
             out_b += align_up(sizeof(float) * (size_t)it.C * it.N, 256);
             if (post && post[i].brk) {
                 in_b += align_up(4 * (size_t)(post[i].n_e + 1), 256) + 2 * align_up(4 * (size_t)(post[i].n_blocks + 1), 256);
-                out_b += align_up(8 * (size_t)it.C * post[i].n_e, 256) + 256;
+                out_b += align_up(8 * (size_t)SS_LOUD_SCRATCH_DOUBLES * it.C * post[i].n_e, 256) + 256;
             }
         }
         if (k >= (size_t)ss_ctx::kSlots) CK(cudaEventSynchronize(sl.ev_free));      // slot's previous chunk fully drained
@@ -1300,7 +1300,7 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
                 li.blk_lo = (const int32_t*)pi; pi += align_up(nb + 4, 256);
                 if (nb) CK(cudaMemcpyAsync(pi, pl.blk_hi, nb, cudaMemcpyHostToDevice, c->s_in));
                 li.blk_hi = (const int32_t*)pi; pi += align_up(nb + 4, 256);
-                li.scratch = (double*)po; po += align_up(8 * (size_t)it.C * pl.n_e, 256);
+                li.scratch = (double*)po; po += align_up(8 * (size_t)SS_LOUD_SCRATCH_DOUBLES * it.C * pl.n_e, 256);
                 li.result = (double*)po; po += 256;
                 res_dev[i] = li.result;
                 li.data = d.out; li.out = d.out;                 // (C, N) stem, normalised in place

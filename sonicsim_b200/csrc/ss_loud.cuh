@@ -41,36 +41,94 @@ struct LoudItem {
     const int* brk;          // n_e + 1 ascending sample indices: the gating blocks' distinct bounds
     const int* blk_lo;       // per gating block j: first elementary interval
     const int* blk_hi;       // per gating block j: one past its last elementary interval
-    double* E;               // scratch, C * n_e interval energies (sum of squares of the K-weighted signal)
+    double* E;               // scratch, kLoudScratch * C * n_e doubles: [0, C n_e) interval energies (sum of squares of
+                             // the K-weighted signal), then the per-interval filter states of the three passes below
     double* result;          // [0] integrated loudness (LUFS, -inf allowed), [1] linear gain applied
     long long stride_n, stride_c;
-    int N, C, n_e, n_blocks, warm, pad_;
+    int N, C, n_e, n_blocks, pad_[2];
     double inv_norm;         // 1 / (T_g * rate)
     double target;           // target LUFS (SonicSim_audio.py:77 `norm`)
 };
+constexpr int kLoudScratch = 16;   // doubles of scratch per (channel, elementary interval)
 
-// Energy of the K-weighted channel over [brk[e], brk[e+1]).  The recursion is started `warm`
-// samples early from rest; the high-pass double pole (r ~ 0.985 at 16 kHz) has decayed below
-// 1e-10 by then, and when the start clamps to sample 0 the state is exact.
-SS_HD double kweight_interval_energy(const LoudItem& it, const KCoef& k, int c, int e) {
+// ---- K-weighting of one channel, EXACT and parallel over the elementary intervals.
+// pyloudnorm filters the whole channel with scipy.signal.lfilter (direct form II transposed, float64), stage by
+// stage, storing each stage back into its float32 array.  The recursion is linear, so the state at the start of
+// interval e is   S_e = M^len(e-1) S_(e-1) + F_(e-1),   F = state at the end of an interval filtered from rest,
+// M = [[-a1, 1], [-a2, 0]].  Three passes, one thread per (channel, interval), each over its own samples only:
+//   pass 1  stage 1 from rest                                  -> F1, and M1^len, M2^len by repeated squaring
+//   pass 2  S1 by the recurrence over the earlier intervals; stage 1 exact, its float32 output through stage 2 from rest -> F2
+//   pass 3  S2 likewise; both stages exact; energy of the float32 output
+// No warm-up approximation: the result differs from lfilter's only by float64 rounding of the state recurrence.
+struct Mat2 { double a, b, c, d; };
+SS_HD Mat2 mat_mul(const Mat2& x, const Mat2& y) {
+    Mat2 r; r.a = x.a * y.a + x.b * y.c; r.b = x.a * y.b + x.b * y.d; r.c = x.c * y.a + x.d * y.c; r.d = x.c * y.b + x.d * y.d;
+    return r;
+}
+SS_HD Mat2 mat_pow(Mat2 m, int n) {
+    Mat2 r; r.a = 1; r.b = 0; r.c = 0; r.d = 1;
+    while (n > 0) { if (n & 1) r = mat_mul(r, m); m = mat_mul(m, m); n >>= 1; }
+    return r;
+}
+SS_HD Mat2 stage_matrix(const KCoef& k, int s) { Mat2 m; m.a = -k.a1[s]; m.b = 1.0; m.c = -k.a2[s]; m.d = 0.0; return m; }
+
+// scratch slots of (channel c, interval e)
+SS_HD double* loud_slot(const LoudItem& it, int which, int c, int e) {
+    // which: 0 E(1) | 1 F1(2) | 2 S1(2) | 3 F2(2) | 4 M1(4) | 5 M2(4)
+    const long long ce = (long long)it.C * it.n_e, i = (long long)c * it.n_e + e;
+    switch (which) {
+        case 0: return it.E + i;
+        case 1: return it.E + ce + 2 * i;
+        case 2: return it.E + 3 * ce + 2 * i;
+        case 3: return it.E + 5 * ce + 2 * i;
+        case 4: return it.E + 7 * ce + 4 * i;
+        default: return it.E + 11 * ce + 4 * i;
+    }
+}
+// state at the start of interval e from the per-interval (M^len, F) of the intervals before it
+SS_HD void state_at(const LoudItem& it, int c, int e, int which_m, int which_f, double& z1, double& z2) {
+    z1 = 0; z2 = 0;
+    for (int q = 0; q < e; ++q) {
+        const double* m = loud_slot(it, which_m, c, q);
+        const double* f = loud_slot(it, which_f, c, q);
+        const double n1 = m[0] * z1 + m[1] * z2 + f[0], n2 = m[2] * z1 + m[3] * z2 + f[1];
+        z1 = n1; z2 = n2;
+    }
+}
+template <int PASS>
+SS_HD void kweight_pass(const LoudItem& it, const KCoef& k, int c, int e) {
     const int start = it.brk[e], end = it.brk[e + 1];
-    int n = start - it.warm; if (n < 0) n = 0;
     const float* p = it.data + (long long)c * it.stride_c;
     double z1a = 0, z2a = 0, z1b = 0, z2b = 0, acc = 0;
-    for (; n < end; ++n) {
-        double x = (double)p[(long long)n * it.stride_n];
+    if (PASS >= 2) {
+        if (PASS == 2) { state_at(it, c, e, 4, 1, z1a, z2a); double* s1 = loud_slot(it, 2, c, e); s1[0] = z1a; s1[1] = z2a; }
+        else { const double* s1 = loud_slot(it, 2, c, e); z1a = s1[0]; z2a = s1[1]; state_at(it, c, e, 5, 3, z1b, z2b); }
+    }
+    for (int n = start; n < end; ++n) {
+        const double x = (double)p[(long long)n * it.stride_n];
         // scipy.signal.lfilter: direct form II transposed, float64; pyloudnorm stores each stage back
         // into the float32 array (meter.py: input_data[:,ch] = filter.apply_filter(...))
-        double y = k.b0[0] * x + z1a;
+        const double y = k.b0[0] * x + z1a;
         z1a = k.b1[0] * x - k.a1[0] * y + z2a;
         z2a = k.b2[0] * x - k.a2[0] * y;
-        double x2 = (double)(float)y;
-        double y2 = k.b0[1] * x2 + z1b;
-        z1b = k.b1[1] * x2 - k.a1[1] * y2 + z2b;
-        z2b = k.b2[1] * x2 - k.a2[1] * y2;
-        if (n >= start) { float yf = (float)y2; acc += (double)(yf * yf); }
+        if (PASS >= 2) {
+            const double x2 = (double)(float)y;
+            const double y2 = k.b0[1] * x2 + z1b;
+            z1b = k.b1[1] * x2 - k.a1[1] * y2 + z2b;
+            z2b = k.b2[1] * x2 - k.a2[1] * y2;
+            if (PASS == 3) { const float yf = (float)y2; acc += (double)(yf * yf); }
+        }
     }
-    return acc;
+    if (PASS == 1) {
+        double* f1 = loud_slot(it, 1, c, e); f1[0] = z1a; f1[1] = z2a;
+        const Mat2 m1 = mat_pow(stage_matrix(k, 0), end - start), m2 = mat_pow(stage_matrix(k, 1), end - start);
+        double* d1 = loud_slot(it, 4, c, e); d1[0] = m1.a; d1[1] = m1.b; d1[2] = m1.c; d1[3] = m1.d;
+        double* d2 = loud_slot(it, 5, c, e); d2[0] = m2.a; d2[1] = m2.b; d2[2] = m2.c; d2[3] = m2.d;
+    } else if (PASS == 2) {
+        double* f2 = loud_slot(it, 3, c, e); f2[0] = z1b; f2[1] = z2b;
+    } else {
+        *loud_slot(it, 0, c, e) = acc;
+    }
 }
 
 SS_HD double channel_gain(int c) { return (c == 3 || c == 4) ? 1.41 : 1.0; }   // pyloudnorm G = [1,1,1,1.41,1.41]

@@ -1,6 +1,6 @@
 // sonicsim_b200 :: ss_loudness.cu - SonicSim_audio.lufs_norm (SonicSim_audio.py:68-81) on the GPU.
-//   k_kweight_energy : one thread per (stem, channel, elementary interval) runs the two K-weighting
-//                      biquads in float64 over its interval (+ warm-up) and accumulates the energy
+//   k_kweight<1,2,3> : one thread per (stem, channel, elementary interval); three passes over the thread's own interval
+//                      give the exact filter state at its start (ss_loud.cuh) and the energy of the K-weighted signal
 //   k_loud_gate      : one thread per stem: block loudness, absolute / relative gates, LUFS, gain
 //   k_loud_scale     : out = gain * data (float4 vectorised)
 #include <math.h>
@@ -11,8 +11,11 @@
 
 using namespace ss;
 
+static_assert(kLoudScratch == SS_LOUD_SCRATCH_DOUBLES, "scratch contract of include/sonicsim_b200.h");
+
+template <int PASS>
 __global__ void __launch_bounds__(128)
-k_kweight_energy(const LoudItem* __restrict__ items, const int* __restrict__ prefix, int n_items, KCoef k) {
+k_kweight(const LoudItem* __restrict__ items, const int* __restrict__ prefix, int n_items, KCoef k) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= prefix[n_items]) return;
     int lo = 0, hi = n_items - 1;
@@ -20,7 +23,7 @@ k_kweight_energy(const LoudItem* __restrict__ items, const int* __restrict__ pre
     const LoudItem& it = items[lo];
     const int local = gid - prefix[lo];
     const int c = local / it.n_e, e = local - c * it.n_e;
-    it.E[(long long)c * it.n_e + e] = kweight_interval_energy(it, k, c, e);
+    kweight_pass<PASS>(it, k, c, e);
 }
 
 __global__ void k_loud_gate(const LoudItem* __restrict__ items, int n_items) {
@@ -60,7 +63,6 @@ static LoudItem to_item(const ss_loud_item& a) {
     it.E = a.scratch; it.result = a.result;
     it.stride_n = a.stride_n; it.stride_c = a.stride_c;
     it.N = a.N; it.C = a.C; it.n_e = a.n_e; it.n_blocks = a.n_blocks;
-    it.warm = (int)ceil(0.128 * a.rate);
     it.inv_norm = 1.0 / (a.block_size * a.rate);
     it.target = a.target_lufs;
     return it;
@@ -94,11 +96,13 @@ extern "C" int ss_loudness_dev(ss_ctx* c, const ss_loud_item* items, int n_items
     const LoudItem* d = (const LoudItem*)c->d_desc[slot];
     const int* dp = (const int*)(c->d_desc[slot] + off_p);
     const KCoef k = make_kcoef(items[0].rate);
-    k_kweight_energy<<<(tot + 127) / 128, 128, 0, stream>>>(d, dp, n_items, k);
+    k_kweight<1><<<(tot + 127) / 128, 128, 0, stream>>>(d, dp, n_items, k);
+    k_kweight<2><<<(tot + 127) / 128, 128, 0, stream>>>(d, dp, n_items, k);
+    k_kweight<3><<<(tot + 127) / 128, 128, 0, stream>>>(d, dp, n_items, k);
     CK(cudaGetLastError());
     k_loud_gate<<<(n_items + 63) / 64, 64, 0, stream>>>(d, n_items);
     CK(cudaGetLastError());
-    c->launches += 2;
+    c->launches += 4;
     if (any_out) {
         dim3 grid(c->sm_count * 2, n_items);
         k_loud_scale<<<grid, 256, 0, stream>>>(d);
@@ -121,7 +125,7 @@ extern "C" int ss_lufs_norm_host(ss_ctx* c, const float* data, float* out, int32
     const size_t o_lo = o_brk + align_up(4 * (size_t)(n_e + 1), 256);
     const size_t o_hi = o_lo + align_up(4 * (size_t)(n_blocks + 1), 256);
     const size_t o_E = o_hi + align_up(4 * (size_t)(n_blocks + 1), 256);
-    const size_t o_res = o_E + align_up(8 * (size_t)C * n_e, 256);
+    const size_t o_res = o_E + align_up(8 * (size_t)kLoudScratch * C * n_e, 256);
     const size_t total = o_res + 256;
     ss_ctx::Slot& sl = c->slot[0];
     CK(cudaStreamSynchronize(c->s_cmp));

@@ -281,12 +281,14 @@ int emu_lufs(const float* data, int N, int C, long long stride_n, long long stri
              double target, const int32_t* brk, int n_e, const int32_t* blk_lo, const int32_t* blk_hi, int n_blocks,
              double* result) {
     LoudItem it; memset(&it, 0, sizeof(it));
-    std::vector<double> E((size_t)C * n_e);
+    std::vector<double> E((size_t)kLoudScratch * C * n_e);
     it.data = data; it.brk = brk; it.blk_lo = blk_lo; it.blk_hi = blk_hi; it.E = E.data(); it.result = result;
     it.stride_n = stride_n; it.stride_c = stride_c; it.N = N; it.C = C; it.n_e = n_e; it.n_blocks = n_blocks;
-    it.warm = (int)ceil(0.128 * rate); it.inv_norm = 1.0 / (block_size * rate); it.target = target;
+    it.inv_norm = 1.0 / (block_size * rate); it.target = target;
     KCoef k = make_kcoef(rate);
-    for (int c = 0; c < C; ++c) for (int e = 0; e < n_e; ++e) E[(size_t)c * n_e + e] = kweight_interval_energy(it, k, c, e);
+    for (int c = 0; c < C; ++c) for (int e = 0; e < n_e; ++e) kweight_pass<1>(it, k, c, e);
+    for (int c = 0; c < C; ++c) for (int e = 0; e < n_e; ++e) kweight_pass<2>(it, k, c, e);
+    for (int c = 0; c < C; ++c) for (int e = 0; e < n_e; ++e) kweight_pass<3>(it, k, c, e);
     loudness_gate(it);
     return 0;
 }

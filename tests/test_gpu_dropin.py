@@ -45,3 +45,52 @@ def test_process_single_call_pattern():
     for a, b in zip(ours, ref):
         assert a.shape == (C, N) and a.dtype == torch.float32
         assert so.rel_rms(a.numpy(), b.numpy()) < TOL
+
+
+def test_numpy_semantics_at_the_boundary():
+    """What NumPy / SciPy do for the reference at SonicSim_moving.py:86-94 and what the drop-in must therefore do too:
+    negative interp_index wraps (idx = -1 pairs the LAST position with the FIRST), non-integer index arrays raise
+    IndexError, float64 inputs give a float64 result (computed in float32 here), more RIRs than waypoints is fine."""
+    from sonicsim_b200 import SonicSim_moving as sm
+    rng = np.random.default_rng(17)
+    P, C, L, N = 6, 2, 700, 20000
+    x, h = so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L)
+    w = rng.random(N).astype(np.float32)
+    # negative indices, with and without the -1 wrap pair
+    for lo in (-1, -2):
+        idx = rng.integers(-P, lo + 1, N)
+        idx[::3] = rng.integers(0, P - 1, len(idx[::3]))
+        ref = so.convolve_moving_receiver(x, h, idx, w)
+        got = sm.convolve_moving_receiver(x, h, idx, w)
+        assert got.dtype == np.float32 and so.rel_rms(got, ref) < TOL
+    with pytest.raises(IndexError):
+        sm.convolve_moving_receiver(x, h, np.full(N, -P - 1), w)
+    with pytest.raises(IndexError):
+        so.convolve_moving_receiver(x, h, np.full(N, -P - 1), w)
+    with pytest.raises(IndexError):
+        sm.convolve_moving_receiver(x, h, np.zeros(N, np.float32), w)                 # float index array
+    with pytest.raises(IndexError):
+        so.convolve_moving_receiver(x, h, np.zeros(N, np.float32), w)
+    # dtype rule
+    idx = np.sort(rng.integers(0, P - 1, N))
+    ref64 = so.convolve_moving_receiver(x.astype(np.float64), h.astype(np.float64), idx, w.astype(np.float64))
+    got64 = sm.convolve_moving_receiver(x.astype(np.float64), h, idx, w)
+    assert ref64.dtype == np.float64 and got64.dtype == np.float64 and so.rel_rms(got64, ref64) < 2e-6
+    assert sm.convolve_moving_receiver(x, h, idx, w.astype(np.float64)).dtype == \
+        so.convolve_moving_receiver(x, h, idx, w.astype(np.float64)).dtype
+    f64 = sm.convolve_fixed_receiver(x[None].astype(np.float64), h[0])
+    assert f64.dtype == so.convolve_fixed_receiver(x[None].astype(np.float64), h[0]).dtype == np.float64
+    # interpolate_moving_audio: RIR count vs waypoint count
+    pos = so.synth_path(rng, P - 2)
+    np.random.seed(4)
+    a = sm.interpolate_moving_audio(torch.from_numpy(x[None]), torch.from_numpy(h[:, None]), pos)          # 6 RIRs, 4 waypoints
+    np.random.seed(4)
+    b = so.interpolate_moving_audio(x[None], h[:, None], pos)
+    assert so.rel_rms(a.numpy(), b) < TOL
+    pos = so.synth_path(rng, P + 2)
+    with pytest.raises(IndexError):
+        np.random.seed(4)
+        sm.interpolate_moving_audio(torch.from_numpy(x[None]), torch.from_numpy(h[:, None]), pos)          # 6 RIRs, 8 waypoints
+    with pytest.raises(IndexError):
+        np.random.seed(4)
+        so.interpolate_moving_audio(x[None], h[:, None], pos)

@@ -162,3 +162,62 @@ def test_oracle_loudness_close_to_torchaudio_bs1770():
             y = signal.lfilter(b, a, y, axis=0)
         ungated = -0.691 + 10.0 * np.log10(np.sum(np.mean(y ** 2, axis=0)))
         assert theirs - ungated > 1.0, (sr, C, ungated, theirs)
+
+
+# ---- pins against the real pyloudnorm 0.1.1: live when the package can be imported, and through the fixture
+# oracle/pin_loudness.py writes when it can.  Neither is available in the authoring image (no network): both skip there
+# and a5 stays "parity unpinned"; on a box that has the package they turn the restated oracle into a pinned one.
+def _golden_lufs():
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lufs_norm.npz")
+    return np.load(p) if os.path.isfile(p) else None
+
+
+def test_oracle_matches_live_pyloudnorm():
+    pyln = pytest.importorskip("pyloudnorm")
+    for seed, N, C, sr in [(11, 160000, 2, 16000), (12, 96000, 5, 48000), (13, 5000, 1, 16000)]:
+        x = stems(seed, N, C, sr)
+        block = 0.4 if N > 0.4 * sr else N / sr
+        ref = pyln.Meter(rate=sr, block_size=block).integrated_loudness(x)
+        assert abs(so.bs1770_integrated_loudness(x, sr, block) - ref) < 1e-9
+        y_ref = pyln.normalize.loudness(x, ref, -17.0)
+        assert so.rel_rms(so.lufs_norm(x, sr, -17.0)[0], y_ref) < 1e-7
+
+
+def test_oracle_matches_pyloudnorm_fixture():
+    g = _golden_lufs()
+    if g is None:
+        pytest.skip("tests/golden/lufs_norm.npz not present (oracle/pin_loudness.py could not import pyloudnorm)")
+    for k in range(int(g["n_cases"])):
+        N, C, sr = int(g[f"N{k}"]), int(g[f"C{k}"]), int(g[f"sr{k}"])
+        x = stems(int(g[f"seed{k}"]), N, C, sr)
+        y, _ = so.lufs_norm(x, sr, -17.0)
+        assert so.rel_rms(y[:: max(1, N // 4096)], g[f"y{k}"]) < 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_lufs_norm_matches_pyloudnorm_fixture():
+    g = _golden_lufs()
+    if g is None:
+        pytest.skip("tests/golden/lufs_norm.npz not present (oracle/pin_loudness.py could not import pyloudnorm)")
+    from sonicsim_b200 import SonicSim_audio as sa
+    for k in range(int(g["n_cases"])):
+        N, C, sr = int(g[f"N{k}"]), int(g[f"C{k}"]), int(g[f"sr{k}"])
+        x = stems(int(g[f"seed{k}"]), N, C, sr)
+        y, _ = sa.lufs_norm(x, sr, -17.0)
+        assert so.rel_rms(y[:: max(1, N // 4096)], g[f"y{k}"]) < 1.2e-5          # 1e-4 dB
+
+
+@pytest.mark.gpu
+def test_gpu_kweighting_state_is_exact_for_long_stems():
+    """The three-pass K-weighting carries the exact filter state into every gating interval: a stem whose loud part is
+    preceded by a strong sub-sonic transient (which a truncated warm-up would forget) still matches the oracle's
+    sequential lfilter to 1e-6 dB."""
+    from sonicsim_b200 import SonicSim_audio as sa
+    sr, N = 16000, 16000 * 20
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((N, 2)) * 0.01).astype(np.float32)
+    x[: sr // 2] += 0.9                                           # DC step: excites the 38 Hz high-pass for seconds
+    ref = so.bs1770_integrated_loudness(x, sr, 0.4)
+    got = sa.integrated_loudness_and_norm(x, sr, 0.4, -20.0)[0]
+    assert abs(got - ref) < 1e-6, (got, ref)
