@@ -247,6 +247,19 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = time.perf_counter() - t_e0
     barrier()
     t_e1 = time.perf_counter()
+    # ---- secondary: the same end-to-end pass with every stem loudness-normalised on the device before its copy out
+    # (SonicSet.py:97-101 calls get_lufs_norm_audio on every rendered stem)
+    plan_l = R.plan_host(h_srcs, h_outs, lufs_targets=[-17.0] * n_src, sr=CFG["sr"])
+    plan_l.run()
+    barrier()
+    n_l = max(2, min(K * I, 8))
+    t_l0 = time.perf_counter()
+    for _ in range(n_l):
+        plan_l.run()
+    torch.cuda.synchronize()
+    lufs_s = (time.perf_counter() - t_l0) / n_l
+    lufs_meas = plan_l.loudness()[0]
+    barrier()
     # ---- copy-only floor of the e2e arm: the same bytes in both directions over PCIe, nothing else, on every rank at
     # the same time (at N >= 4 the GPUs share PCIe switches / host memory and the floor itself rises)
     n_floor = max(2, min(K * I, 12))
@@ -297,14 +310,18 @@ def run_ours(args, rank, local_rank, world):
         alg_per_launch = pass_alg * n_prof / max(n_pairs, 1)
         achieved = alg_per_launch / k_render_s / 1e9 if k_render_s > 0 else 0.0
         achieved_path = step_alg * K / dev_s / 1e9              # whole hot path over the timed region itself
-        traffic, traffic_note, ncu_extra = None, "no ncu capture found (profiles/ncu_traffic.json)", None
+        traffic, traffic_note, ncu_extra, traffic_parts = None, "no ncu capture found (profiles/ncu_traffic.json)", None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             ncu_extra = {k: tj["k_render"].get(k) for k in ("issue_slots_busy_pct", "fma_pipe_active_pct", "dram_pct_of_peak")}
-            per_src = (tj["k_render"]["dram_read_mb"] + tj["k_render"]["dram_write_mb"]) * 1e6 / tj["sources_per_launch"]
-            traffic = per_src * (n_src * n_prof / max(n_pairs, 1))
-            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one k_render launch from `ncu --set full` "
-                            "(%s; cold L2 per replay), scaled to this launch size" % tj["tag"])
+            mb = lambda k: (tj[k]["dram_read_mb"] + tj[k]["dram_write_mb"]) * 1e6 / tj["sources_per_launch"]
+            scale = n_src * n_prof / max(n_pairs, 1)
+            traffic = (mb("k_render") + mb("k_prepare")) * scale
+            traffic_parts = {"k_render": mb("k_render") * scale, "k_prepare": mb("k_prepare") * scale}
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one k_prepare + k_render launch pair from `ncu --set "
+                            "full` (%s; cold L2 per replay: the spectra k_prepare writes and k_render reads make an HBM round "
+                            "trip there that they do not make in the timed run), scaled to this launch size; compare with "
+                            "alg_bytes_per_launch" % tj["tag"])
         except Exception:
             pass
         # instruction-issue view of the same launch (the kernel's actual limiter): warp instructions of one launch
@@ -322,8 +339,29 @@ def run_ours(args, rank, local_rank, world):
                                  % (tj["tag"], sm_count, mhz)}
         except Exception:
             pass
+        # L1 / shared-memory data-pipe view (the other resource the kernel runs against): bytes one
+        # transform moves through an SM's 128 B/clk data pipe - staged spectra written by the copy engine and read once
+        # (2 x 96 KB), two exchanges through the FFT buffer (2 x (64 + 64) KB), inter-pass twiddles (2 x 15 x 8 B x 256
+        # threads), the (4096,) float32 output row
+        pipe = None
+        try:
+            n_tr = sum(int(np.ceil(np.diff(b) / 4096.0).sum()) * C for _, _, b in items) * n_prof / max(n_pairs, 1)
+            per_tr = 2 * 96 * 1024 + 2 * 128 * 1024 + 2 * 15 * 8 * 256 + 4096 * 4
+            pk = sm_count * 128 * mhz * 1e6
+            pipe = {"transforms_per_launch": n_tr, "bytes_per_transform": per_tr, "achieved": n_tr * per_tr / k_render_s / 1e9,
+                    "peak": pk / 1e9, "unit": "GB/s", "frac": n_tr * per_tr / k_render_s / pk,
+                    "note": "algorithmic bytes through the SMs' L1 / shared-memory data pipes (%d SMs x 128 B/clk x %.0f MHz); "
+                            "bank conflicts and the copy engine's own arbitration come on top" % (sm_count, mhz)}
+        except Exception:
+            pass
         in_b = sum(x.nbytes + h.nbytes + b.nbytes for x, h, b in items) * I
         out_b = n_src * C * N * 4 * I
+        scene_lufs = {"value": U * N / CFG["sr"] / lufs_s, "unit": UNIT, "ms_per_pass": 1e3 * lufs_s,
+                      "extra_ms_per_pass_vs_e2e": 1e3 * (lufs_s - e2e_s / K / I), "rank": 0,
+                      "first_stem_lufs_before": lufs_meas[0], "first_stem_gain": lufs_meas[1],
+                      "what": "e2e pass (rank 0) with lufs_norm fused behind the render: K-weighting (3 exact passes), gating, "
+                              "gain and in-place scale of every (6, 480000) stem on the device before its D2H copy; "
+                              "Renderer.plan_host(..., lufs_targets).run() -> ss_render_host_ex"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * dev_max / K, "higher_is_better": True, "scaling": "weak",
@@ -348,11 +386,12 @@ def run_ours(args, rank, local_rank, world):
                                        "ranks at once (max over ranks); the e2e arm cannot be faster than this on this box",
                     "api": "sonicsim_b200.render.Renderer.plan_host(...).run() -> ss_render_host",
                     "bit_identical_to_device_arm": same, "checksum": checksum},
+            "scene_lufs": scene_lufs,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
-                         "limiter": "fp32 issue + shared-memory/barrier latency, not DRAM (see DESIGN.md section 4)",
-                         "ncu_k_render": ncu_extra, "issue": issue,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_parts": traffic_parts, "traffic_note": traffic_note, "peak_source": peak_src,
+                         "limiter": "instruction issue (~0.6 of the slots) and the SMs' L1 / shared-memory data pipe (~0.65) together, not DRAM (see DESIGN.md section 4)",
+                         "ncu_k_render": ncu_extra, "issue": issue, "l1_data_pipe": pipe,
                          "alg_bytes_per_launch": alg_per_launch, "kernel_ms": 1e3 * k_render_s,
                          "k_prepare_ms": 1e3 * k_spec_s, "path_achieved": achieved_path,
                          "path_frac": achieved_path / peak, "launch_pairs_timed": int(n_pairs),

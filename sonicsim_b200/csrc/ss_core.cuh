@@ -168,6 +168,27 @@ SS_HD void tw_load(const float2* tab, float2 (&w)[16]) {
     for (int r = 1; r < 16; ++r)
         w[r] = dirw<INV>((STRIDE == 256 && r >= SS_TWC_STREAM_FROM) ? ldg_stream(tab + r * STRIDE) : ldg_cached(tab + r * STRIDE));
 }
+// only rows 1, 2, 4, 8 of the table are loaded, the other eleven twiddles are products of them
+// (w_3 = w_1 w_2, ..., w_(8 + r) = w_r w_8): 11 complex multiplies instead of 11 loads through the L1 data pipe
+template <bool INV, int STRIDE>
+SS_HD void tw_load_pow(const float2* tab, float2 (&w)[16]) {
+    w[0] = make_float2(1.f, 0.f);
+    w[1] = dirw<INV>(ldg_cached(tab + 1 * STRIDE));
+    w[2] = dirw<INV>(ldg_cached(tab + 2 * STRIDE));
+    w[4] = dirw<INV>(ldg_cached(tab + 4 * STRIDE));
+    w[8] = dirw<INV>(ldg_cached(tab + 8 * STRIDE));
+    w[3] = cmul(w[1], w[2]); w[5] = cmul(w[1], w[4]); w[6] = cmul(w[2], w[4]); w[7] = cmul(w[3], w[4]);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) w[8 + r] = cmul(w[r], w[8]);
+}
+// all fifteen from w1 alone (already direction-adjusted): w2 = w1^2, w4 = w2^2, w8 = w4^2, the rest products
+SS_HD void tw_from_w1(float2 w1, float2 (&w)[16]) {
+    w[0] = make_float2(1.f, 0.f);
+    w[1] = w1; w[2] = cmul(w1, w1); w[4] = cmul(w[2], w[2]); w[8] = cmul(w[4], w[4]);
+    w[3] = cmul(w[1], w[2]); w[5] = cmul(w[1], w[4]); w[6] = cmul(w[2], w[4]); w[7] = cmul(w[3], w[4]);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) w[8 + r] = cmul(w[r], w[8]);
+}
 template <bool INV>
 SS_HD void fft16_w(float2 (&v)[16], const float2 (&w)[16]) {
     fft4_tw<INV, false>(v[0], v[4], v[8], v[12], w[0], w[4], w[8], w[12]);
@@ -175,10 +196,24 @@ SS_HD void fft16_w(float2 (&v)[16], const float2 (&w)[16]) {
     for (int b = 1; b < 4; ++b) fft4_tw<INV, true>(v[b], v[b + 4], v[b + 8], v[b + 12], w[b], w[b + 4], w[b + 8], w[b + 12]);
     fft16_level2<INV>(v);
 }
+// Every transform of the library (forward and inverse, every kernel variant, and the CPU emulation) gets its
+// inter-pass twiddles the same way, so that a source renders to the same bits whatever batch it is part of.
+#ifndef SS_TWPOW
+#define SS_TWPOW 1            // 1: rows 1, 2, 4, 8 of the table + 11 products (round 2: the L1 data pipe is the scarcer
+                              //    resource, k_render 124.7 -> 119.3 us); 0: all fifteen loaded from the table (round 1)
+#endif
+template <bool INV, int STRIDE>
+SS_HD void tw_get(const float2* tab, float2 (&w)[16]) {
+#if SS_TWPOW
+    tw_load_pow<INV, STRIDE>(tab, w);
+#else
+    tw_load<INV, STRIDE>(tab, w);
+#endif
+}
 template <bool INV, int STRIDE>
 SS_HD void fft16_tw(float2 (&v)[16], const float2* tab) {
     float2 w[16];
-    tw_load<INV, STRIDE>(tab, w);
+    tw_get<INV, STRIDE>(tab, w);
     fft16_w<INV>(v, w);
 }
 // register slot that holds output index r after fft16

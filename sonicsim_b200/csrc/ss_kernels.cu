@@ -395,6 +395,23 @@ constexpr int kItemLane = 7 * 32;     // thread that prefetches work items and i
 #ifndef SS_F_LATECHECK
 #define SS_F_LATECHECK 0      // 1: the last-warp test (and the X / Hp copy) after the first pass-C butterfly
 #endif
+#ifndef SS_F_TWREG
+#define SS_F_TWREG 0          // 1: no table access inside the loop at all: w1 of pass B and exp(2 pi i t / 8192) live in
+                              //    registers, pass C's w1 is its square (measured: slower, 123 registers; breaks the
+                              //    same-bits-in-every-kernel property of tw_get)
+#endif
+#if SS_F_TWREG
+#define SS_TW_B(w) tw_from_w1(w1b, w)
+#define SS_TW_C(w) tw_from_w1(cmul(wtc, wtc), w)
+#else
+#define SS_TW_B(w) tw_get<true, 16>(T.twB + (t & 15), w)
+#define SS_TW_C(w) tw_get<true, 256>(T.twC + t, w)
+#endif
+#ifndef SS_F_XKEEP
+#define SS_F_XKEEP 1          // 1: a CTA renders a contiguous range of items (the channels of a block are neighbours) and
+                              // keeps the dry spectrum X in its own buffer while consecutive items share it; Hp and Hq
+                              // both land in the FFT buffer
+#endif
 #ifndef SS_F_FAKE
 #define SS_F_FAKE 0           // timing experiments only (WRONG results): 1 no pass B, 2 no staged-spectra reads, 4 no global stores, 8 no bulk copies
 #endif
@@ -438,17 +455,31 @@ k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_p
                                                         // [2] staged spectra consumed, [3] pass-B inputs loaded (8 warps)
     __shared__ unsigned s_drained;                      // warps that have finished their pass-C loads, cumulative
     float2* const fftbuf = smem;
+#if SS_F_XKEEP
+    float2* const sX = smem + kPadF;                    // its own buffer: survives the transform
+    float2* const sHp = smem;
+    float2* const sHq = smem + kSpec;
+#else
     float2* const sX = smem;
     float2* const sHp = smem + kSpec;
     float2* const sHq = smem + kPadF;
+#endif
     const Tables T{g_tw, g_twB, g_twC};
     const int t = threadIdx.x, lane = t & 31;
-    const int grid = (int)gridDim.x;
     // table length: known on the host when it built the tables, otherwise written by k_blocks
     const int n_items = n_items_host >= 0 ? n_items_host : *n_items_ptr;
+#if SS_F_XKEEP
+    const int per = n_items / (int)gridDim.x, rem = n_items % (int)gridDim.x;
+    const int n_k = per + ((int)blockIdx.x < rem ? 1 : 0);              // transforms of this CTA: a contiguous range
+    const int grid = 1;                                                 // distance between this CTA's items
+    if (n_k <= 0) return;
+    const RItem* const my_items = items + (size_t)blockIdx.x * per + ((int)blockIdx.x < rem ? (int)blockIdx.x : rem);
+#else
+    const int grid = (int)gridDim.x;
     const int n_k = (n_items - (int)blockIdx.x + grid - 1) / grid;      // transforms of this CTA
     if (n_k <= 0) return;
     const RItem* const my_items = items + blockIdx.x;
+#endif
 
     if (t == kItemLane) {
         mbar_init(&s_bar[0], 1);
@@ -461,16 +492,28 @@ k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_p
         if (n_k > 1) s_item[1] = my_items[grid];
         const float2* const hp = s_item[0].H0 + (size_t)s_item[0].p_lo * s_item[0].pstride;
         fence_proxy_async();
+#if SS_F_XKEEP
+        mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
+        bulk_g2s(sHp, hp, kSpecBytes, &s_bar[0]);
+        bulk_g2s(sHq, hp + s_item[0].pstride, kSpecBytes, &s_bar[0]);
+        mbar_expect_tx(&s_bar[1], kSpecBytes);
+        bulk_g2s(sX, s_item[0].X, kSpecBytes, &s_bar[1]);
+#else
         mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
         bulk_g2s(sX, s_item[0].X, kSpecBytes, &s_bar[0]);
         bulk_g2s(sHp, hp, kSpecBytes, &s_bar[0]);
         mbar_expect_tx(&s_bar[1], kSpecBytes);
         bulk_g2s(sHq, hp + s_item[0].pstride, kSpecBytes, &s_bar[1]);
+#endif
     }
     __syncthreads();
 
     Regs32 R;
     float2 w[16];
+#if SS_F_TWREG
+    const float2 wtc = dirw<true>(ldg_cached(T.tw + t));                     // exp(+2 pi i t / 8192): closing radix-2, and w1 of pass C squared
+    const float2 w1b = dirw<true>(ldg_cached(T.twB + 16 + (t & 15)));       // exp(+2 pi i (t & 15) / 256): w1 of pass B
+#endif
     XDesc unused; unused.kparts = 1; unused.Hq = nullptr; unused.X = nullptr; unused.Hp = nullptr;
     unsigned ph = 0;
     for (int k = 0; k < n_k; ++k) {
@@ -498,9 +541,17 @@ k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_p
         if (t == kItemLane) {
             if (k + 1 < n_k && !(SS_F_FAKE & 8)) {        // Hq of transform k + 1 (its item became visible at barrier B4 of k - 1)
                 const RItem& nx = s_item[(k + 1) % 3];
+#if SS_F_XKEEP
+                if (nx.X != s_item[k % 3].X) {            // next item belongs to another block: its dry spectrum
+                    fence_proxy_async();
+                    mbar_expect_tx(&s_bar[1], kSpecBytes);
+                    bulk_g2s(sX, nx.X, kSpecBytes, &s_bar[1]);
+                } else mbar_arrive(&s_bar[1]);            // same block, other channel: X stays where it is
+#else
                 fence_proxy_async();
                 mbar_expect_tx(&s_bar[1], kSpecBytes);
                 bulk_g2s(sHq, nx.H0 + (size_t)(nx.p_lo + 1) * nx.pstride, kSpecBytes, &s_bar[1]);
+#endif
             }
             // item k + 2 into the slot of item k - 1 (last read in the output stage of k - 1, which every warp has left)
             if (k + 2 < n_k) item_prefetch(&s_item[(k + 2) % 3], my_items + (size_t)(k + 2) * grid);
@@ -508,13 +559,13 @@ k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_p
         passA_store(fftbuf, passA_jA(t), R.a);
         passA_store(fftbuf, passA_jB(t), R.b);
 #if SS_F_HOIST
-        tw_load<true, 16>(T.twB + (t & 15), w);
+        SS_TW_B(w);
 #endif
 #if !(SS_F_FAKE & 1)
         __syncthreads();                                  // B2: pass A -> pass B exchange
         load2_ab(t, fftbuf, R);
 #if !SS_F_HOIST
-        tw_load<true, 16>(T.twB + (t & 15), w);
+        SS_TW_B(w);
 #endif
 #if SS_F_SPLIT
         __syncwarp();
@@ -531,13 +582,13 @@ k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_p
         passB_store(fftbuf, t + 256, R.b);
 #endif
 #if SS_F_HOIST
-        tw_load<true, 256>(T.twC + t, w);
+        SS_TW_C(w);
 #endif
         if (t == kItemLane) item_prefetch_wait();         // item k + 2 has landed; visible to all behind B4
         __syncthreads();                                  // B4: pass B -> pass C exchange
         load2_ab(t, fftbuf, R);
 #if !SS_F_HOIST
-        tw_load<true, 256>(T.twC + t, w);
+        SS_TW_C(w);
 #endif
 #if SS_F_FENCEALL
         fence_proxy_async();
@@ -553,15 +604,24 @@ k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_p
             const RItem& nx = s_item[(k + 1) % 3];
             fence_proxy_async();
             mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
+#if SS_F_XKEEP
+            bulk_g2s(sHp, nx.H0 + (size_t)nx.p_lo * nx.pstride, kSpecBytes, &s_bar[0]);
+            bulk_g2s(sHq, nx.H0 + (size_t)(nx.p_lo + 1) * nx.pstride, kSpecBytes, &s_bar[0]);
+#else
             bulk_g2s(sX, nx.X, kSpecBytes, &s_bar[0]);
             bulk_g2s(sHp, nx.H0 + (size_t)nx.p_lo * nx.pstride, kSpecBytes, &s_bar[0]);
+#endif
         }
         ph ^= 1;
 #if !SS_F_LATECHECK
         fft16_w<true>(R.a, w);                            // pass C
 #endif
         fft16_w<true>(R.b, w);
+#if SS_F_TWREG
+        render_phase3_close_w(R, wtc);
+#else
         render_phase3_close(t, R, T);
+#endif
 #if SS_F_FAKE & 4
         if (R.a[0].x + R.a[5].y + R.a[9].x + R.a[15].y == 123.456f) render_epilogue_item(t, s_item[k % 3], R);
 #else

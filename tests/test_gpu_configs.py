@@ -69,6 +69,15 @@ def test_cfg4_long_rir_full_size_properties():
     n_cut = int(np.searchsorted(idx, 2))
     ref64 = so.convolve_moving_exact_f64(x[:n_cut], h1, idx[:n_cut], w[:n_cut])
     assert so.rel_rms(y1[:, :n_cut], ref64) < TOL
+    # ... and three more windows of the full-length render against the same float64 ground truth: one in the middle
+    # that straddles a waypoint, one a third of the way in, and the very end.  y[n] only depends on x[n - L + 1 .. n],
+    # so a window is evaluated from a slice that starts L - 1 samples earlier and those first samples are dropped.
+    mid_wp = int(np.searchsorted(idx, P // 2))                       # first sample of segment P // 2
+    for n0, n1 in [(mid_wp - 20000, mid_wp + 20000), (N // 3, N // 3 + 30000), (N - 40000, N)]:
+        a = n0 - (L - 1)
+        ref_w = so.convolve_moving_exact_f64(x[a:n1], h1, idx[a:n1], w[a:n1])[:, L - 1:]
+        assert ref_w.shape == (C, n1 - n0)
+        assert so.rel_rms(y1[:, n0:n1], ref_w) < TOL, (n0, n1)
 
 
 def test_cfg5_binaural_dual_render():
