@@ -231,6 +231,11 @@ int ss_get_profile(ss_ctx* ctx, double* ms_spectra, double* ms_render, int64_t* 
  * negative ss_status (SS_ERR_NOMEM: max_blocks too small). */
 int ss_debug_plan(const ss_source* item, int32_t* blocks_out, int32_t max_blocks, int32_t* aligned_out);
 
+/* Test hook, pure host code: how a batch whose items need bytes[i] of scratch is cut into launch groups under `budget`
+ * (ss_set_chunk_bytes): cuts_out receives the first item of every chunk followed by n.  Returns the number of values
+ * written, or a negative ss_status (SS_ERR_NOMEM: max_cuts too small). */
+int ss_debug_chunks(const int64_t* bytes, int32_t n, int64_t budget, int32_t* cuts_out, int32_t max_cuts);
+
 /* pinned host memory helpers (cudaHostAlloc) for callers without torch */
 int ss_host_alloc(void** ptr, int64_t bytes);
 void ss_host_free(void* ptr);

@@ -137,6 +137,7 @@ def load():
         lib.ss_overlap_dev.argtypes = [vp, vp, vp, i32, i64, i64, vp]
         lib.ss_overlap_host.argtypes = [vp, vp, vp, i32, i64, i64]
         lib.ss_dry_assemble_dev.argtypes = [vp, ctypes.POINTER(SsDryClip), ctypes.c_int, vp, i64, vp]
+        lib.ss_debug_chunks.argtypes = [vp, i32, i64, vp, i32]
         lib.ss_debug_plan.argtypes = [ctypes.POINTER(SsSource), vp, i32, ctypes.POINTER(i32)]
         lib.ss_launch_count.argtypes = [vp]
         lib.ss_launch_count.restype = i64
@@ -155,7 +156,7 @@ def load():
 EXPORTS = ["ss_version", "ss_strerror", "ss_last_cuda_error", "ss_create", "ss_destroy",
            "ss_set_chunk_bytes", "ss_render_dev", "ss_plan_create", "ss_plan_run", "ss_plan_is_graph", "ss_plan_destroy", "ss_render_host", "ss_render_host_ex", "ss_convolve_fixed_receiver",
            "ss_convolve_moving_receiver", "ss_loudness_dev", "ss_lufs_norm_host", "ss_mix_scratch_doubles", "ss_mix_dev", "ss_mix_host",
-           "ss_mix_host_ex", "ss_overlap_dev", "ss_overlap_host", "ss_dry_assemble_dev", "ss_debug_plan", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
+           "ss_mix_host_ex", "ss_overlap_dev", "ss_overlap_host", "ss_dry_assemble_dev", "ss_debug_plan", "ss_debug_chunks", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
            "ss_host_free"]
 
 

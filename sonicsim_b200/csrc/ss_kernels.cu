@@ -105,8 +105,18 @@ k_rir_absmax(const Source* __restrict__ srcs) {
     const int part = blockIdx.x % kNormParts;
     const size_t total = (size_t)S.P * S.C * S.L;
     float m = 0.f;
-    for (size_t i = (size_t)part * blockDim.x + threadIdx.x; i < total; i += (size_t)kNormParts * blockDim.x)
-        m = fmaxf(m, fabsf(S.rir[i]));
+    if ((((uintptr_t)S.rir) & 15) == 0) {               // 16-byte loads over the aligned bulk, scalar tail
+        const float4* r4 = (const float4*)S.rir;
+        const size_t n4 = total >> 2;
+        for (size_t i = (size_t)part * blockDim.x + threadIdx.x; i < n4; i += (size_t)kNormParts * blockDim.x) {
+            const float4 v = r4[i];
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
+        if (part == 0 && threadIdx.x < (total & 3)) m = fmaxf(m, fabsf(S.rir[(n4 << 2) + threadIdx.x]));
+    } else {
+        for (size_t i = (size_t)part * blockDim.x + threadIdx.x; i < total; i += (size_t)kNormParts * blockDim.x)
+            m = fmaxf(m, fabsf(S.rir[i]));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     __shared__ float s_m[8];
@@ -843,7 +853,7 @@ static size_t spectra_bytes(const ss_source& it) {
     const Shape sh = shape_of(it);
     return ((size_t)it.P * it.C * sh.K + sh.nblk_max) * kSpec * sizeof(float2) + (size_t)sh.max_items * sizeof(RItem) +
            align_up(sizeof(Block) * (size_t)sh.nblk_max, 256) + align_up(sizeof(double) * (size_t)it.P, 256) + 256 +
-           ((it.flags & SS_RIR_NORMALIZE) ? 256 : 0);
+           ((it.flags & SS_RIR_NORMALIZE) ? 512 : 0);
 }
 
 // Host-side twin of k_blocks for one source whose trajectory bounds are visible on the host.
@@ -947,7 +957,7 @@ static void chunk_describe(const ss_source* items, int first, int last, char* hb
         s.K = sh.K; s.nb = sh.nb; s.mode = it.mode; s.aligned = sh.aligned; s.nblk_max = sh.nblk_max;
         s.hspec = (float2*)scratch; scratch += (size_t)s.P * s.C * s.K * kSpec * sizeof(float2);
         s.xspec = (float2*)scratch; scratch += (size_t)s.nblk_max * kSpec * sizeof(float2);
-        if (it.flags & SS_RIR_NORMALIZE) { s.norm_part = (const float*)scratch; scratch += 256; any_norm = true; }
+        if (it.flags & SS_RIR_NORMALIZE) { s.norm_part = (const float*)scratch; scratch += 512; any_norm = true; }
         if (host_tables) {
             // tables live in the descriptor block itself: filled here, copied with it
             Block* hb_blocks = (Block*)(hbase + tab_off);
@@ -1047,28 +1057,49 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
 }
 
 // split [0, n) into chunks whose spectra fit the L2-sized budget
-static void make_chunks(const ss_ctx* c, const ss_source* items, int n, std::vector<int>& cuts, int64_t budget = 0) {
-    if (budget <= 0) budget = c->chunk_bytes;
+static void make_chunks_bytes(const std::vector<size_t>& sb, int64_t budget, std::vector<int>& cuts) {
+    const int n = (int)sb.size();
     // greedy pass: how many chunks does the budget need ...
-    std::vector<size_t> sb(n);
     size_t total = 0, acc = 0;
     int n_chunks = 1;
     for (int i = 0; i < n; ++i) {
-        sb[i] = spectra_bytes(items[i]);
         total += sb[i];
         if (acc > 0 && acc + sb[i] > (size_t)budget) { ++n_chunks; acc = 0; }
         acc += sb[i];
     }
     // ... then cut at equal shares of the total, so that the last chunk is not a runt (7,7,7,7,4 -> 6,6,7,6,7):
-    // equal chunks keep both streams of the overlap equally busy
+    // equal chunks keep the streams of the overlap equally busy.  A chunk never exceeds the budget (measured from
+    // the bytes accumulated at its own first item) unless a single item does.
     cuts.clear(); cuts.push_back(0);
     acc = 0;
+    size_t chunk_start = 0;                            // bytes in front of the current chunk
     for (int i = 0; i < n; ++i) {
         const size_t target = total * cuts.size() / n_chunks;
-        if (i > cuts.back() && (acc + sb[i] / 2 > target || acc - (cuts.size() > 1 ? total * (cuts.size() - 1) / n_chunks : 0) + sb[i] > (size_t)budget)) cuts.push_back(i);
+        if (i > cuts.back() && (acc + sb[i] / 2 > target || acc - chunk_start + sb[i] > (size_t)budget)) {
+            cuts.push_back(i);
+            chunk_start = acc;
+        }
         acc += sb[i];
     }
     cuts.push_back(n);
+}
+static void make_chunks(const ss_ctx* c, const ss_source* items, int n, std::vector<int>& cuts, int64_t budget = 0) {
+    if (budget <= 0) budget = c->chunk_bytes;
+    std::vector<size_t> sb(n);
+    for (int i = 0; i < n; ++i) sb[i] = spectra_bytes(items[i]);
+    make_chunks_bytes(sb, budget, cuts);
+}
+// Test hook (pure host): the chunking of items whose scratch needs are `bytes[i]` under `budget`; cuts_out receives
+// the first item of every chunk plus n (at most max_cuts values); returns the number of values written or a negative status.
+extern "C" int ss_debug_chunks(const int64_t* bytes, int32_t n, int64_t budget, int32_t* cuts_out, int32_t max_cuts) {
+    if (!bytes || !cuts_out || n <= 0 || budget <= 0) return SS_ERR_INVALID;
+    std::vector<size_t> sb(n);
+    for (int i = 0; i < n; ++i) { if (bytes[i] <= 0) return SS_ERR_INVALID; sb[i] = (size_t)bytes[i]; }
+    std::vector<int> cuts;
+    make_chunks_bytes(sb, budget, cuts);
+    if ((int)cuts.size() > max_cuts) return SS_ERR_NOMEM;
+    for (size_t i = 0; i < cuts.size(); ++i) cuts_out[i] = cuts[i];
+    return (int)cuts.size();
 }
 
 static int validate_dev_items(const ss_source* items, int n_items) {

@@ -95,40 +95,53 @@ SS_HD void state_at(const LoudItem& it, int c, int e, int which_m, int which_f, 
         z1 = n1; z2 = n2;
     }
 }
+// filter state of one thread = one (channel, interval)
+struct KwState { double z1a, z2a, z1b, z2b, acc; };
+template <int PASS>
+SS_HD void kw_begin(const LoudItem& it, int c, int e, KwState& st) {
+    st.z1a = 0; st.z2a = 0; st.z1b = 0; st.z2b = 0; st.acc = 0;
+    if (PASS == 2) { state_at(it, c, e, 4, 1, st.z1a, st.z2a); double* s1 = loud_slot(it, 2, c, e); s1[0] = st.z1a; s1[1] = st.z2a; }
+    if (PASS == 3) { const double* s1 = loud_slot(it, 2, c, e); st.z1a = s1[0]; st.z2a = s1[1]; state_at(it, c, e, 5, 3, st.z1b, st.z2b); }
+}
+template <int PASS>
+SS_HD void kw_sample(const KCoef& k, float xf, KwState& st) {
+    const double x = (double)xf;
+    // scipy.signal.lfilter: direct form II transposed, float64; pyloudnorm stores each stage back
+    // into the float32 array (meter.py: input_data[:,ch] = filter.apply_filter(...))
+    const double y = k.b0[0] * x + st.z1a;
+    st.z1a = k.b1[0] * x - k.a1[0] * y + st.z2a;
+    st.z2a = k.b2[0] * x - k.a2[0] * y;
+    if (PASS >= 2) {
+        const double x2 = (double)(float)y;
+        const double y2 = k.b0[1] * x2 + st.z1b;
+        st.z1b = k.b1[1] * x2 - k.a1[1] * y2 + st.z2b;
+        st.z2b = k.b2[1] * x2 - k.a2[1] * y2;
+        if (PASS == 3) { const float yf = (float)y2; st.acc += (double)(yf * yf); }
+    }
+}
+template <int PASS>
+SS_HD void kw_end(const LoudItem& it, const KCoef& k, int c, int e, const KwState& st) {
+    if (PASS == 1) {
+        const int len = it.brk[e + 1] - it.brk[e];
+        double* f1 = loud_slot(it, 1, c, e); f1[0] = st.z1a; f1[1] = st.z2a;
+        const Mat2 m1 = mat_pow(stage_matrix(k, 0), len), m2 = mat_pow(stage_matrix(k, 1), len);
+        double* d1 = loud_slot(it, 4, c, e); d1[0] = m1.a; d1[1] = m1.b; d1[2] = m1.c; d1[3] = m1.d;
+        double* d2 = loud_slot(it, 5, c, e); d2[0] = m2.a; d2[1] = m2.b; d2[2] = m2.c; d2[3] = m2.d;
+    } else if (PASS == 2) {
+        double* f2 = loud_slot(it, 3, c, e); f2[0] = st.z1b; f2[1] = st.z2b;
+    } else {
+        *loud_slot(it, 0, c, e) = st.acc;
+    }
+}
+// one thread, samples read straight from memory (CPU emulation; the CUDA kernel feeds kw_sample from coalesced tiles)
 template <int PASS>
 SS_HD void kweight_pass(const LoudItem& it, const KCoef& k, int c, int e) {
     const int start = it.brk[e], end = it.brk[e + 1];
     const float* p = it.data + (long long)c * it.stride_c;
-    double z1a = 0, z2a = 0, z1b = 0, z2b = 0, acc = 0;
-    if (PASS >= 2) {
-        if (PASS == 2) { state_at(it, c, e, 4, 1, z1a, z2a); double* s1 = loud_slot(it, 2, c, e); s1[0] = z1a; s1[1] = z2a; }
-        else { const double* s1 = loud_slot(it, 2, c, e); z1a = s1[0]; z2a = s1[1]; state_at(it, c, e, 5, 3, z1b, z2b); }
-    }
-    for (int n = start; n < end; ++n) {
-        const double x = (double)p[(long long)n * it.stride_n];
-        // scipy.signal.lfilter: direct form II transposed, float64; pyloudnorm stores each stage back
-        // into the float32 array (meter.py: input_data[:,ch] = filter.apply_filter(...))
-        const double y = k.b0[0] * x + z1a;
-        z1a = k.b1[0] * x - k.a1[0] * y + z2a;
-        z2a = k.b2[0] * x - k.a2[0] * y;
-        if (PASS >= 2) {
-            const double x2 = (double)(float)y;
-            const double y2 = k.b0[1] * x2 + z1b;
-            z1b = k.b1[1] * x2 - k.a1[1] * y2 + z2b;
-            z2b = k.b2[1] * x2 - k.a2[1] * y2;
-            if (PASS == 3) { const float yf = (float)y2; acc += (double)(yf * yf); }
-        }
-    }
-    if (PASS == 1) {
-        double* f1 = loud_slot(it, 1, c, e); f1[0] = z1a; f1[1] = z2a;
-        const Mat2 m1 = mat_pow(stage_matrix(k, 0), end - start), m2 = mat_pow(stage_matrix(k, 1), end - start);
-        double* d1 = loud_slot(it, 4, c, e); d1[0] = m1.a; d1[1] = m1.b; d1[2] = m1.c; d1[3] = m1.d;
-        double* d2 = loud_slot(it, 5, c, e); d2[0] = m2.a; d2[1] = m2.b; d2[2] = m2.c; d2[3] = m2.d;
-    } else if (PASS == 2) {
-        double* f2 = loud_slot(it, 3, c, e); f2[0] = z1b; f2[1] = z2b;
-    } else {
-        *loud_slot(it, 0, c, e) = acc;
-    }
+    KwState st;
+    kw_begin<PASS>(it, c, e, st);
+    for (int n = start; n < end; ++n) kw_sample<PASS>(k, p[(long long)n * it.stride_n], st);
+    kw_end<PASS>(it, k, c, e, st);
 }
 
 SS_HD double channel_gain(int c) { return (c == 3 || c == 4) ? 1.41 : 1.0; }   // pyloudnorm G = [1,1,1,1.41,1.41]

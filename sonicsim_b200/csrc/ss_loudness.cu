@@ -13,17 +13,62 @@ using namespace ss;
 
 static_assert(kLoudScratch == SS_LOUD_SCRATCH_DOUBLES, "scratch contract of include/sonicsim_b200.h");
 
+// One thread per (stem, channel, elementary interval), a warp = 32 consecutive work items.  Every thread walks its
+// own interval sequentially (the recurrence), so reading the samples directly would touch 32 different cache lines per
+// load instruction; instead the warp moves 32 x 32-sample tiles through shared memory: row r of the tile is loaded by
+// all lanes at once (128 contiguous bytes of work item r's interval when the stem is channel-major), then lane j
+// consumes row j.
 template <int PASS>
 __global__ void __launch_bounds__(128)
 k_kweight(const LoudItem* __restrict__ items, const int* __restrict__ prefix, int n_items, KCoef k) {
+    __shared__ float tile[4][32][33];
+    __shared__ const float* row_ptr[4][32];           // first sample of work item r's interval
+    __shared__ int row_len[4][32];
+    __shared__ long long row_stride[4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= prefix[n_items]) return;
-    int lo = 0, hi = n_items - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (prefix[mid] <= gid) lo = mid; else hi = mid - 1; }
-    const LoudItem& it = items[lo];
-    const int local = gid - prefix[lo];
-    const int c = local / it.n_e, e = local - c * it.n_e;
-    kweight_pass<PASS>(it, k, c, e);
+    const bool live = gid < prefix[n_items];
+    int lo = 0, c = 0, e = 0, len = 0;
+    row_ptr[warp][lane] = nullptr; row_len[warp][lane] = 0; row_stride[warp][lane] = 1;
+    if (live) {
+        int hi = n_items - 1;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (prefix[mid] <= gid) lo = mid; else hi = mid - 1; }
+        const LoudItem& it = items[lo];
+        const int local = gid - prefix[lo];
+        c = local / it.n_e; e = local - c * it.n_e;
+        const int start = it.brk[e];
+        len = it.brk[e + 1] - start;
+        row_ptr[warp][lane] = it.data + (long long)c * it.stride_c + (long long)start * it.stride_n;
+        row_len[warp][lane] = len;
+        row_stride[warp][lane] = it.stride_n;
+    }
+    KwState st;
+    if (live) kw_begin<PASS>(items[lo], c, e, st);
+    // longest interval of the warp decides the trip count (intervals are 0.1 s, the last of a stem may be shorter)
+    int maxlen = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_xor_sync(0xffffffffu, maxlen, o); maxlen = v > maxlen ? v : maxlen; }
+    __syncwarp();
+    // lane l fetches sample s0 + l of every row r: 128 contiguous bytes per row for a channel-major stem
+    float nxt[32];
+    auto fetch = [&](int s0) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int n = s0 + lane;
+            nxt[r] = n < row_len[warp][r] ? row_ptr[warp][r][(long long)n * row_stride[warp][r]] : 0.f;
+        }
+    };
+    fetch(0);
+    for (int s0 = 0; s0 < maxlen; s0 += 32) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) tile[warp][r][lane] = nxt[r];
+        __syncwarp();
+        if (s0 + 32 < maxlen) fetch(s0 + 32);          // in flight while this tile is consumed
+        const int cnt = len - s0 < 32 ? len - s0 : 32;
+        if (live) for (int i = 0; i < cnt; ++i) kw_sample<PASS>(k, tile[warp][lane][i], st);
+        __syncwarp();
+    }
+    if (live) kw_end<PASS>(items[lo], k, c, e, st);
 }
 
 __global__ void k_loud_gate(const LoudItem* __restrict__ items, int n_items) {

@@ -44,7 +44,7 @@ struct Source {
     int nblk_max;          // table size: nb (grid) or nb + P - 1 (aligned)
     int pad_[1];
 };
-constexpr int kNormParts = 32;     // CTAs (partial maxima) per normalised source in k_rir_absmax
+constexpr int kNormParts = 128;    // CTAs (partial maxima) per normalised source in k_rir_absmax
 
 // One unit of k_render work: one block of channel c (static: channels c, c+1), written by k_prepare
 // so that k_render never searches trajectories, prefix tables or the Source array.

@@ -149,3 +149,35 @@ def test_host_block_planner_invariants_and_choice():
         assert pos == N
         if aligned:
             assert len(blocks) == cost_aligned
+
+
+def test_chunking_respects_the_budget_and_balances():
+    """ss_debug_chunks (pure host): every chunk fits the scratch budget unless a single item is bigger, chunks are
+    contiguous and cover the batch, equal items are split into near-equal chunks (the budget rule used to be
+    measured from an ideal cut position, which let chunks of mixed item sizes grow to twice the budget)."""
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        n = int(rng.integers(1, 60))
+        kind = trial % 3
+        if kind == 0:
+            b = np.full(n, 13 << 20, np.int64)
+        elif kind == 1:
+            b = rng.integers(1 << 20, 40 << 20, n).astype(np.int64)
+        else:
+            b = np.where(rng.random(n) < 0.2, 90 << 20, 2 << 20).astype(np.int64)
+        budget = int(rng.integers(20 << 20, 120 << 20))
+        cuts = np.zeros(n + 1, np.int32)
+        k = lib.ss_debug_chunks(b.ctypes.data, n, budget, cuts.ctypes.data, n + 1)
+        assert k >= 2
+        cuts = cuts[:k]
+        assert cuts[0] == 0 and cuts[-1] == n and np.all(np.diff(cuts) > 0)
+        sizes = [int(b[a:c].sum()) for a, c in zip(cuts[:-1], cuts[1:])]
+        for (a, c), sz in zip(zip(cuts[:-1], cuts[1:]), sizes):
+            assert sz <= budget or c - a == 1, (trial, sz, budget)
+    # 32 equal items, 7 per budget: 5 chunks of 6-7 items, not 7,7,7,7,4
+    b = np.full(32, 13 << 20, np.int64)
+    cuts = np.zeros(33, np.int32)
+    k = lib.ss_debug_chunks(b.ctypes.data, 32, 96 << 20, cuts.ctypes.data, 33)
+    d = np.diff(cuts[:k])
+    assert k == 6 and d.min() >= 6 and d.max() <= 7
