@@ -340,13 +340,13 @@ def run_ours(args, rank, local_rank, world):
         except Exception:
             pass
         # L1 / shared-memory data-pipe view (the other resource the kernel runs against): bytes one
-        # transform moves through an SM's 128 B/clk data pipe - staged spectra written by the copy engine and read once
-        # (2 x 96 KB), two exchanges through the FFT buffer (2 x (64 + 64) KB), inter-pass twiddles (2 x 15 x 8 B x 256
-        # threads), the (4096,) float32 output row
+        # transform moves through an SM's 128 B/clk data pipe - staged spectra written by the copy engine (Hp, Hq every
+        # transform, X once per block = every C-th) and read once (96 KB), two exchanges through the FFT buffer
+        # (2 x (64 + 64) KB), inter-pass twiddles (2 x 4 table rows x 8 B x 256 threads), the (4096,) float32 output row
         pipe = None
         try:
             n_tr = sum(int(np.ceil(np.diff(b) / 4096.0).sum()) * C for _, _, b in items) * n_prof / max(n_pairs, 1)
-            per_tr = 2 * 96 * 1024 + 2 * 128 * 1024 + 2 * 15 * 8 * 256 + 4096 * 4
+            per_tr = (2.0 + 1.0 / C) * 32 * 1024 + 96 * 1024 + 2 * 128 * 1024 + 2 * 4 * 8 * 256 + 4096 * 4
             pk = sm_count * 128 * mhz * 1e6
             pipe = {"transforms_per_launch": n_tr, "bytes_per_transform": per_tr, "achieved": n_tr * per_tr / k_render_s / 1e9,
                     "peak": pk / 1e9, "unit": "GB/s", "frac": n_tr * per_tr / k_render_s / pk,
@@ -388,7 +388,7 @@ def run_ours(args, rank, local_rank, world):
                     "bit_identical_to_device_arm": same, "checksum": checksum},
             "scene_lufs": scene_lufs,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_render_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_parts": traffic_parts, "traffic_note": traffic_note, "peak_source": peak_src,
                          "limiter": "instruction issue (~0.6 of the slots) and the SMs' L1 / shared-memory data pipe (~0.65) together, not DRAM (see DESIGN.md section 4)",
                          "ncu_k_render": ncu_extra, "issue": issue, "l1_data_pipe": pipe,
