@@ -1,7 +1,7 @@
 // sonicsim_b200 :: ss_loudness.cu - SonicSim_audio.lufs_norm (SonicSim_audio.py:68-81) on the GPU.
 //   k_kweight<1,2,3> : one thread per (stem, channel, elementary interval); three passes over the thread's own interval
 //                      give the exact filter state at its start (ss_loud.cuh) and the energy of the K-weighted signal
-//   k_loud_gate      : one thread per stem: block loudness, absolute / relative gates, LUFS, gain
+//   k_loud_gate      : one CTA per stem: block loudness, absolute / relative gates (fixed-order reductions), LUFS, gain
 //   k_loud_scale     : out = gain * data (float4 vectorised)
 #include <math.h>
 #include <string.h>
@@ -71,9 +71,68 @@ k_kweight(const LoudItem* __restrict__ items, const int* __restrict__ prefix, in
     if (live) kw_end<PASS>(items[lo], k, c, e, st);
 }
 
-__global__ void k_loud_gate(const LoudItem* __restrict__ items, int n_items) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_items) loudness_gate(items[i]);
+// Gating (pyloudnorm meter.py integrated_loudness; ss_loud.cuh loudness_gate is the one-thread statement of it that the
+// CPU emulation runs): one CTA per stem, the gating blocks dealt to its threads, per-channel sums over the blocks that
+// pass a gate reduced in a fixed order (warp shuffles, then the warps in turn) so that runs are bit-reproducible.
+constexpr int kGateThreads = 128;
+__device__ __forceinline__ double gate_reduce(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0;
+    for (int w = 0; w < kGateThreads / 32; ++w) r += sh[w];
+    return r;                                            // the same value in every thread
+}
+__global__ void __launch_bounds__(kGateThreads) k_loud_gate(const LoudItem* __restrict__ items, int n_items) {
+    __shared__ double sh[kGateThreads / 32];
+    const LoudItem& it = items[blockIdx.x];
+    const int nb = it.n_blocks, C = it.C;
+    double zmean[8];
+    double gamma_r = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        double zs[8], cnt = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) zs[c] = 0;
+        for (int j = threadIdx.x; j < nb; j += kGateThreads) {
+            double zc[8], s = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c < C) {
+                    double z = 0;
+                    for (int e = it.blk_lo[j]; e < it.blk_hi[j]; ++e) z += it.E[(long long)c * it.n_e + e];
+                    zc[c] = z * it.inv_norm;
+                    s += channel_gain(c) * zc[c];
+                }
+            }
+            const double l = -0.691 + 10.0 * log10(s);
+            const bool ok = pass == 0 ? (l >= -70.0) : (l > gamma_r && l > -70.0);
+            if (ok) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) if (c < C) zs[c] += zc[c];
+                cnt += 1.0;
+            }
+        }
+        const double n_ok = gate_reduce(cnt, sh);
+        double s = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c < C) {
+                const double tot = gate_reduce(zs[c], sh);
+                // pass 0: mean of an empty list is NaN (nothing passes the relative gate then); pass 1: nan_to_num -> 0
+                zmean[c] = n_ok > 0 ? tot / n_ok : (pass == 0 ? NAN : 0.0);
+                s += channel_gain(c) * zmean[c];
+            }
+        }
+        if (pass == 0) gamma_r = -0.691 + 10.0 * log10(s) - 10.0;
+        else if (threadIdx.x == 0) {
+            const double lufs = -0.691 + 10.0 * log10(s);                      // log10(0) = -inf
+            const double used = isinf(lufs) ? -40.0 : lufs;                     // SonicSim_audio.py:73-75
+            it.result[0] = lufs;
+            it.result[1] = pow(10.0, (it.target - used) / 20.0);               // pyln.normalize.loudness
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -145,7 +204,7 @@ extern "C" int ss_loudness_dev(ss_ctx* c, const ss_loud_item* items, int n_items
     k_kweight<2><<<(tot + 127) / 128, 128, 0, stream>>>(d, dp, n_items, k);
     k_kweight<3><<<(tot + 127) / 128, 128, 0, stream>>>(d, dp, n_items, k);
     CK(cudaGetLastError());
-    k_loud_gate<<<(n_items + 63) / 64, 64, 0, stream>>>(d, n_items);
+    k_loud_gate<<<n_items, kGateThreads, 0, stream>>>(d, n_items);
     CK(cudaGetLastError());
     c->launches += 4;
     if (any_out) {
