@@ -31,7 +31,9 @@ struct ss_ctx {
     // host path
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
     struct Slot { char* d_in = nullptr; size_t in_cap = 0; char* d_out = nullptr; size_t out_cap = 0;
-                  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_free = nullptr; } slot[4];
+                  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_free = nullptr, ev_rend = nullptr; } slot[4];
+    // loudness post-processing of the host path: pinned block (results | gating tables) and its device twin
+    char* h_post = nullptr; char* d_post = nullptr; size_t h_post_cap = 0;
     static const int kSlots = 4;   // H2D may run up to 3 chunks ahead of the D2H that frees a slot
     int64_t launches = 0;
     bool single_stream = false;   // experiment knob (SS_SINGLE_STREAM=1): no chunk overlap

@@ -702,6 +702,7 @@ static int init_ctx(ss_ctx* c, int device) {
     for (int i = 0; i < ss_ctx::kSlots; ++i) {
         CK(cudaEventCreateWithFlags(&c->slot[i].ev_in, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->slot[i].ev_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->slot[i].ev_rend, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->slot[i].ev_free, cudaEventDisableTiming));
     }
     c->single_stream = getenv("SS_SINGLE_STREAM") != nullptr;
@@ -742,8 +743,11 @@ extern "C" void ss_destroy(ss_ctx* c) {
         if (c->slot[i].d_out) cudaFree(c->slot[i].d_out);
         if (c->slot[i].ev_in) cudaEventDestroy(c->slot[i].ev_in);
         if (c->slot[i].ev_done) cudaEventDestroy(c->slot[i].ev_done);
+        if (c->slot[i].ev_rend) cudaEventDestroy(c->slot[i].ev_rend);
         if (c->slot[i].ev_free) cudaEventDestroy(c->slot[i].ev_free);
     }
+    if (c->h_post) cudaFreeHost(c->h_post);
+    if (c->d_post) cudaFree(c->d_post);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -1338,6 +1342,55 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
     std::vector<ss_source> dev(n_items);
     std::vector<ss_loud_item> loud;
     std::vector<double*> res_dev(n_items, nullptr);
+    // loudness: (a) the gating tables of all sources that share them (same host arrays = same clip length, the normal
+    // case) are uploaded once per call from a pinned staging copy; (b) the two result doubles of every stem come back
+    // into pinned memory - a copy into the caller's pageable array would block the host until the stream gets
+    // there and serialise the whole pipeline; (c) the loudness kernels of consecutive chunks run on rotating side
+    // streams: their grids are small and latency-bound (~0.5 ms per chunk), three of them overlap each other, the
+    // next chunk's render and the copies
+    struct Tab { const int32_t *brk, *lo, *hi; int n_e, n_blocks; const int32_t *d_brk, *d_lo, *d_hi; };
+    std::vector<Tab> tabs;
+    std::vector<int> tab_of(n_items, -1);
+    if (post) {
+        size_t tab_bytes = 0;
+        for (int i = 0; i < n_items; ++i) {
+            if (!post[i].brk) continue;
+            int t = -1;
+            for (size_t q = 0; q < tabs.size(); ++q)
+                if (tabs[q].brk == post[i].brk && tabs[q].lo == post[i].blk_lo && tabs[q].hi == post[i].blk_hi &&
+                    tabs[q].n_e == post[i].n_e && tabs[q].n_blocks == post[i].n_blocks) { t = (int)q; break; }
+            if (t < 0) {
+                Tab nt = {post[i].brk, post[i].blk_lo, post[i].blk_hi, post[i].n_e, post[i].n_blocks, nullptr, nullptr, nullptr};
+                tabs.push_back(nt); t = (int)tabs.size() - 1;
+                tab_bytes += align_up(4 * (size_t)(nt.n_e + 1), 256) + 2 * align_up(4 * (size_t)(nt.n_blocks + 1), 256);
+            }
+            tab_of[i] = t;
+        }
+        const size_t res_bytes = align_up(2 * sizeof(double) * (size_t)n_items, 256);
+        if (tab_bytes + res_bytes > c->h_post_cap) {
+            CK(cudaDeviceSynchronize());
+            if (c->h_post) CK(cudaFreeHost(c->h_post));
+            if (c->d_post) CK(cudaFree(c->d_post));
+            c->h_post = nullptr; c->d_post = nullptr; c->h_post_cap = 0;
+            const size_t cap = align_up((tab_bytes + res_bytes) * 2, 4096);
+            CK(cudaHostAlloc((void**)&c->h_post, cap, cudaHostAllocDefault));
+            CK(cudaMalloc((void**)&c->d_post, cap));
+            c->h_post_cap = cap;
+        }
+        size_t off = res_bytes;                              // [0, res_bytes): results (host side only)
+        for (auto& t : tabs) {
+            size_t nb = 4 * (size_t)(t.n_e + 1);
+            memcpy(c->h_post + off, t.brk, nb); t.d_brk = (const int32_t*)(c->d_post + off); off += align_up(nb, 256);
+            nb = 4 * (size_t)t.n_blocks;
+            if (nb) memcpy(c->h_post + off, t.lo, nb);
+            t.d_lo = (const int32_t*)(c->d_post + off); off += align_up(nb + 4, 256);
+            if (nb) memcpy(c->h_post + off, t.hi, nb);
+            t.d_hi = (const int32_t*)(c->d_post + off); off += align_up(nb + 4, 256);
+        }
+        if (off > res_bytes)
+            CK(cudaMemcpyAsync(c->d_post + res_bytes, c->h_post + res_bytes, off - res_bytes, cudaMemcpyHostToDevice, c->s_in));
+    }
+    double* const h_res = post ? (double*)c->h_post : nullptr;
     // the pipeline proper; any failure falls through to the stream synchronisation below, so that no copy is
     // still reading or writing the caller's buffers when this function returns
     auto pipeline = [&]() -> int {
@@ -1352,10 +1405,8 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
             if (it.mode == SS_MOVING_BOUNDS) in_b += align_up(sizeof(int32_t) * (size_t)it.P, 256);
             if (it.mode == SS_MOVING_INDEXED) in_b += 2 * align_up(4 * (size_t)it.N, 256);
             out_b += align_up(sizeof(float) * (size_t)it.C * it.N, 256);
-            if (post && post[i].brk) {
-                in_b += align_up(4 * (size_t)(post[i].n_e + 1), 256) + 2 * align_up(4 * (size_t)(post[i].n_blocks + 1), 256);
+            if (post && post[i].brk)
                 out_b += align_up(8 * (size_t)SS_LOUD_SCRATCH_DOUBLES * it.C * post[i].n_e, 256) + 256;
-            }
         }
         if (k >= (size_t)ss_ctx::kSlots) CK(cudaEventSynchronize(sl.ev_free));      // slot's previous chunk fully drained
         if ((rc = ensure(&sl.d_in, &sl.in_cap, in_b)) != SS_OK) break;
@@ -1384,13 +1435,8 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
             if (post && post[i].brk) {
                 const ss_post_lufs& pl = post[i];
                 ss_loud_item li; memset(&li, 0, sizeof(li));
-                nb = 4 * (size_t)(pl.n_e + 1);
-                CK(cudaMemcpyAsync(pi, pl.brk, nb, cudaMemcpyHostToDevice, c->s_in)); li.brk = (const int32_t*)pi; pi += align_up(nb, 256);
-                nb = 4 * (size_t)pl.n_blocks;
-                if (nb) CK(cudaMemcpyAsync(pi, pl.blk_lo, nb, cudaMemcpyHostToDevice, c->s_in));
-                li.blk_lo = (const int32_t*)pi; pi += align_up(nb + 4, 256);
-                if (nb) CK(cudaMemcpyAsync(pi, pl.blk_hi, nb, cudaMemcpyHostToDevice, c->s_in));
-                li.blk_hi = (const int32_t*)pi; pi += align_up(nb + 4, 256);
+                const Tab& tb = tabs[tab_of[i]];
+                li.brk = tb.d_brk; li.blk_lo = tb.d_lo; li.blk_hi = tb.d_hi;
                 li.scratch = (double*)po; po += align_up(8 * (size_t)SS_LOUD_SCRATCH_DOUBLES * it.C * pl.n_e, 256);
                 li.result = (double*)po; po += 256;
                 res_dev[i] = li.result;
@@ -1405,16 +1451,21 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
         rc = launch_chunk(c, dev.data(), first, last, c->s_cmp);
         if (rc != SS_OK) break;
         if (!loud.empty()) {
-            rc = ss_loudness_dev(c, loud.data(), (int)loud.size(), (void*)c->s_cmp);
+            cudaStream_t s_l = c->s_aux[k % ss_ctx::kAux];
+            CK(cudaEventRecord(sl.ev_rend, c->s_cmp));
+            CK(cudaStreamWaitEvent(s_l, sl.ev_rend, 0));
+            rc = ss_loudness_dev(c, loud.data(), (int)loud.size(), (void*)s_l);
             if (rc != SS_OK) break;
+            CK(cudaEventRecord(sl.ev_done, s_l));
+        } else {
+            CK(cudaEventRecord(sl.ev_done, c->s_cmp));
         }
-        CK(cudaEventRecord(sl.ev_done, c->s_cmp));
         CK(cudaStreamWaitEvent(c->s_out, sl.ev_done, 0));
         for (int i = first; i < last; ++i) {
             CK(cudaMemcpyAsync(items[i].out, dev[i].out, sizeof(float) * (size_t)items[i].C * items[i].N,
                                cudaMemcpyDeviceToHost, c->s_out));
-            if (res_dev[i] && post[i].result)
-                CK(cudaMemcpyAsync(post[i].result, res_dev[i], 2 * sizeof(double), cudaMemcpyDeviceToHost, c->s_out));
+            if (res_dev[i])
+                CK(cudaMemcpyAsync(h_res + 2 * i, res_dev[i], 2 * sizeof(double), cudaMemcpyDeviceToHost, c->s_out));
         }
         CK(cudaEventRecord(sl.ev_free, c->s_out));
         // the next chunk's H2D into the *other* slot may start now; it must not overtake the
@@ -1423,9 +1474,14 @@ extern "C" int ss_render_host_ex(ss_ctx* c, const ss_source* items, int n_items,
     return rc;
     };
     const int rc = pipeline();
-    cudaError_t e1 = cudaStreamSynchronize(c->s_in), e2 = cudaStreamSynchronize(c->s_cmp), e3 = cudaStreamSynchronize(c->s_out);
+    cudaError_t e1 = cudaStreamSynchronize(c->s_in), e2 = cudaStreamSynchronize(c->s_cmp), e3 = cudaSuccess;
+    if (post) for (int i = 0; i < ss_ctx::kAux; ++i) { cudaError_t e = cudaStreamSynchronize(c->s_aux[i]); if (e3 == cudaSuccess) e3 = e; }
+    cudaError_t e4 = cudaStreamSynchronize(c->s_out);
     if (rc != SS_OK) return rc;
-    CK(e1); CK(e2); CK(e3);
+    CK(e1); CK(e2); CK(e3); CK(e4);
+    if (post)
+        for (int i = 0; i < n_items; ++i)
+            if (res_dev[i] && post[i].result) { post[i].result[0] = h_res[2 * i]; post[i].result[1] = h_res[2 * i + 1]; }
     return SS_OK;
 }
 
