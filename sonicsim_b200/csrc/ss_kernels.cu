@@ -15,9 +15,11 @@
 //   k_render  : persistent CTAs; per transform Z = sum_part X[b-part] (H[p] + i H[p+1]) from spectra the
 //               bulk-copy engine staged in shared memory one transform ahead; one 8192-point inverse FFT
 //               gives both positions' convolutions as Re / Im; the closing radix-2 is fused with the
-//               per-sample lerp and the (C, N) store.  <LONG>: RIR partitions >= 1 (staged one after the other);
-//               <FAST>: all-aligned chunk.
-// Consecutive chunks rotate through three streams / scratch buffers so that they overlap.
+//               per-sample lerp and the (C, N) store.  <LONG>: RIR partitions >= 1 (staged one after the other).
+//   k_render_fast : the same for all-aligned chunks (one item = one transform), see its own header below
+//   k_rir_absmax  : optional, SS_RIR_NORMALIZE: global abs-max of a source's RIR tensor for k_prepare's row loads
+// Consecutive chunks rotate through three streams / scratch buffers so that they overlap; a bound batch (ss_plan_*)
+// captures all of it into one CUDA graph.
 // fp32 throughout (the reference is float32 end to end), no cuFFT.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -378,18 +380,19 @@ k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr, i
 
 // ----------------------------------------------------------------------------- k_render_fast
 // The all-aligned chunk (every source a compact trajectory with L <= 4096: BASELINE configs[1] / [2]): one item = one
-// transform that packs the positions (s, s + 1) of the block's segment.  Same phases as k_render; what differs is how
-// the 8 warps of a CTA synchronise and who feeds the bulk-copy engine:
-//   * two CTA-wide barriers per transform (pass A -> B and pass B -> C exchanges through the FFT buffer).  The two
-//     write-after-read hazards of the in-place buffer (staged spectra -> pass-A stores, pass-B loads -> pass-B stores)
-//     are split barriers: a warp *arrives* on an mbarrier as soon as its loads are done, computes its two radix-16
-//     butterflies, and only then waits - by which time the other warps have normally arrived;
-//   * no serial producer section.  Work items are final (k_prepare wrote pointers, sample range, segment start and
-//     1 / length), prefetched two transforms ahead by one lane with cp.async.  The copy of the next transform's X / Hp
-//     into the FFT buffer is issued by whichever warp is the LAST to finish its pass-C loads (a shared counter tells),
-//     so nobody waits for the buffer to drain; its Hq copy by one lane right after the first split barrier;
-//   * the 15 inter-pass twiddles of passes B and C are the same for both butterflies of a thread and independent of
-//     the data: they are loaded ahead of the CTA-wide barrier, while the 64 data registers are dead.
+// transform that packs the positions (s, s + 1) of the block's segment.  Same phases as k_render; what differs is who
+// feeds the bulk-copy engine and how many bytes pass through the SM's L1 / shared-memory data pipe, which together with
+// the issue slots is what the kernel runs against (profiles/EXPERIMENTS.md):
+//   * a CTA renders a CONTIGUOUS range of items: the channels of a block are neighbours and share the dry spectrum X,
+//     which lives in its own 32 KB buffer and is copied only when the next item belongs to another block (one lane
+//     of warp 7, right after the staged spectra have been consumed);
+//   * the filter spectra Hp, Hq of the next transform land in the FFT buffer itself; their copy is issued by whichever
+//     warp is the LAST to finish its pass-C loads (a shared counter tells), so nobody waits for the buffer to drain;
+//   * no serial producer section: work items are final (k_prepare wrote pointers, sample range, segment start and
+//     1 / length) and prefetched two transforms ahead with cp.async;
+//   * inter-pass twiddles: 4 table rows + 11 products per pass (tw_get) instead of 15 loads.
+// Measured and left as knobs (default off): split arrive / wait mbarriers instead of two of the four CTA barriers,
+// twiddle loads hoisted above the exchange barriers, twiddles from registers only - none of them moves the kernel.
 constexpr int kItemLane = 7 * 32;     // thread that prefetches work items and issues the Hq copies (not warp 0, whose
                                       // thread 0 already carries the DC / Nyquist words)
 // experiment knobs (profiles/EXPERIMENTS.md, round 2)

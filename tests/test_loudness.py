@@ -221,3 +221,43 @@ def test_gpu_kweighting_state_is_exact_for_long_stems():
     ref = so.bs1770_integrated_loudness(x, sr, 0.4)
     got = sa.integrated_loudness_and_norm(x, sr, 0.4, -20.0)[0]
     assert abs(got - ref) < 1e-6, (got, ref)
+
+
+# ---- EBU Tech 3341 "minimum requirements" signals for the integrated loudness (the cases pyloudnorm's own test
+# suite checks with the EBU wav files): synthesised here, expected values from the specification, +-0.1 LU.
+def _ebu_case(case, sr=48000):
+    def tone(dbfs, seconds, f=1000.0):
+        t = np.arange(int(seconds * sr)) / sr
+        s = (10.0 ** (dbfs / 20.0)) * np.sin(2 * np.pi * f * t)
+        return np.stack([s, s], 1)
+    if case == 1:
+        return tone(-23.0, 20), -23.0
+    if case == 2:
+        return tone(-33.0, 20), -33.0
+    if case == 3:                                   # relative gate: the quiet parts must be ignored
+        return np.concatenate([tone(-36.0, 10), tone(-23.0, 60), tone(-36.0, 10)]), -23.0
+    if case == 4:                                   # absolute gate as well
+        return np.concatenate([tone(-72.0, 10), tone(-36.0, 10), tone(-23.0, 60), tone(-36.0, 10), tone(-72.0, 10)]), -23.0
+    if case == 5:
+        return np.concatenate([tone(-26.0, 20), tone(-20.0, 20.1), tone(-26.0, 20)]), -23.0
+    raise ValueError(case)
+
+
+@pytest.mark.parametrize("case", [1, 2, 3, 4, 5])
+def test_oracle_and_emulated_kernels_on_ebu_3341_signals(emu, case):
+    x, want = _ebu_case(case)
+    x = x.astype(np.float32)
+    got = so.bs1770_integrated_loudness(x, 48000, 0.4)
+    assert abs(got - want) < 0.1, (case, got)
+    got_emu, _ = emu.lufs(x, 48000, 0.4, target=-23.0)
+    assert abs(got_emu - got) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [1, 3, 4, 5])
+def test_gpu_loudness_on_ebu_3341_signals(case):
+    from sonicsim_b200 import SonicSim_audio as sa
+    x, want = _ebu_case(case)
+    x = x.astype(np.float32)
+    got = sa.integrated_loudness_and_norm(x, 48000, 0.4, -23.0, want_output=False)[0]
+    assert abs(got - want) < 0.1 and abs(got - so.bs1770_integrated_loudness(x, 48000, 0.4)) < 1e-4
