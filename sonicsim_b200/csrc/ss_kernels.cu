@@ -147,8 +147,11 @@ struct PrepParams {
 };
 static_assert(sizeof(PrepParams) <= 4000, "kernel parameter space");
 
+#ifndef SS_PREP_MINB
+#define SS_PREP_MINB 2        // resident CTAs per SM the register allocation of k_prepare aims at (3 fits shared memory)
+#endif
 template <bool INL>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, SS_PREP_MINB)
 k_prepare(const Source* __restrict__ srcs_g, const int* __restrict__ prefix_g, int n_src, RItem* __restrict__ items,
           const __grid_constant__ PrepParams pp) {
     extern __shared__ float2 smem[];
