@@ -54,6 +54,21 @@ __device__ __forceinline__ float noise_at(const MixItem& it, long long e) {
     return __fadd_rn(__fadd_rn(f, b), n);
 }
 
+// 16-byte path of the three streaming passes: element count a multiple of 4, every row 16-byte aligned, no overlap_audio
+// shift (whose +-D neighbours need not be aligned)
+__device__ __forceinline__ bool mix_vec_ok(const MixItem& it) {
+    return it.delay <= 0 && (it.E & 3) == 0 &&
+           ((((uintptr_t)it.spk) | ((uintptr_t)it.noise) | ((uintptr_t)it.mix) | ((uintptr_t)it.spk_out)) & 15) == 0;
+}
+__device__ __forceinline__ float4 noise_sum4(const MixItem& it, long long q) {
+    float4 n = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = 0; m < it.M; ++m) {
+        const float4 v = ((const float4*)(it.noise + (long long)m * it.E))[q];
+        n.x += v.x; n.y += v.y; n.z += v.z; n.w += v.w;
+    }
+    return n;
+}
+
 // pass 1: sum of squares of every speaker stem and of the summed noise
 __global__ void __launch_bounds__(256) k_mix_energy(const MixItem* __restrict__ items) {
     __shared__ double sh[8];
@@ -61,6 +76,17 @@ __global__ void __launch_bounds__(256) k_mix_energy(const MixItem* __restrict__ 
     double acc[kMaxStems + 1];
 #pragma unroll
     for (int i = 0; i <= kMaxStems; ++i) acc[i] = 0;
+    if (mix_vec_ok(it)) {
+        for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < (it.E >> 2); q += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+            for (int s = 0; s < kMaxStems; ++s) if (s < it.S) {
+                const float4 v = ((const float4*)(it.spk + (long long)s * it.E))[q];
+                acc[s] += (double)(v.x * v.x) + (double)(v.y * v.y) + (double)(v.z * v.z) + (double)(v.w * v.w);
+            }
+            const float4 n = noise_sum4(it, q);
+            acc[kMaxStems] += (double)(n.x * n.x) + (double)(n.y * n.y) + (double)(n.z * n.z) + (double)(n.w * n.w);
+        }
+    } else
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < it.E; e += (long long)gridDim.x * blockDim.x) {
 #pragma unroll
         for (int s = 0; s < kMaxStems; ++s) if (s < it.S) { float v = it.spk[(long long)s * it.E + e]; acc[s] += (double)(v * v); }
@@ -111,6 +137,17 @@ __global__ void __launch_bounds__(256) k_mix_speech_energy(const MixItem* __rest
 #pragma unroll
     for (int s = 0; s < kMaxStems; ++s) gf[s] = s < it.S ? (float)g[s] : 0.f;
     double acc = 0;
+    if (mix_vec_ok(it)) {
+        for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < (it.E >> 2); q += (long long)gridDim.x * blockDim.x) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int s = 0; s < kMaxStems; ++s) if (s < it.S) {
+                const float4 a = ((const float4*)(it.spk + (long long)s * it.E))[q];
+                v.x += a.x * gf[s]; v.y += a.y * gf[s]; v.z += a.z * gf[s]; v.w += a.w * gf[s];
+            }
+            acc += (double)(v.x * v.x) + (double)(v.y * v.y) + (double)(v.z * v.z) + (double)(v.w * v.w);
+        }
+    } else
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < it.E; e += (long long)gridDim.x * blockDim.x) {
         float v = 0.f;
 #pragma unroll
@@ -133,15 +170,33 @@ __global__ void __launch_bounds__(256) k_mix_write(const MixItem* __restrict__ i
     float gf[kMaxStems];
 #pragma unroll
     for (int s = 0; s < kMaxStems; ++s) gf[s] = s < it.S ? (float)g[s] : 0.f;
+    if (mix_vec_ok(it)) {
+        for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < (it.E >> 2); q += (long long)gridDim.x * blockDim.x) {
+            float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int s = 0; s < kMaxStems; ++s) if (s < it.S) {
+                float4 v = ((const float4*)(it.spk + (long long)s * it.E))[q];
+                v.x = __fmul_rn(v.x, gf[s]); v.y = __fmul_rn(v.y, gf[s]); v.z = __fmul_rn(v.z, gf[s]); v.w = __fmul_rn(v.w, gf[s]);
+                if (it.spk_out) ((float4*)(it.spk_out + (long long)s * it.E))[q] = v;
+                sp.x += v.x; sp.y += v.y; sp.z += v.z; sp.w += v.w;
+            }
+            const float4 n = noise_sum4(it, q);
+            float4 o;
+            o.x = __fadd_rn(sp.x, __fmul_rn(n.x, gn)); o.y = __fadd_rn(sp.y, __fmul_rn(n.y, gn));
+            o.z = __fadd_rn(sp.z, __fmul_rn(n.z, gn)); o.w = __fadd_rn(sp.w, __fmul_rn(n.w, gn));
+            ((float4*)it.mix)[q] = o;
+        }
+        return;
+    }
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < it.E; e += (long long)gridDim.x * blockDim.x) {
         float sp = 0.f;
 #pragma unroll
         for (int s = 0; s < kMaxStems; ++s) if (s < it.S) {
-            float v = it.spk[(long long)s * it.E + e] * gf[s];
+            float v = __fmul_rn(it.spk[(long long)s * it.E + e], gf[s]);        // products and sums rounded separately, as torch does
             if (it.spk_out) it.spk_out[(long long)s * it.E + e] = v;
             sp += v;
         }
-        it.mix[e] = sp + noise_at(it, e) * gn;
+        it.mix[e] = __fadd_rn(sp, __fmul_rn(noise_at(it, e), gn));
     }
 }
 
