@@ -125,7 +125,7 @@ int ss_convolve_moving_receiver(ss_ctx* ctx, const float* source_audio, const fl
  * bounds are computed by the caller exactly as pyloudnorm does (Python float expressions
  * truncated with int()), and passed as `brk` = the sorted distinct bounds (n_e + 1 values) plus,
  * per gating block j, the range [blk_lo[j], blk_hi[j]) of elementary intervals it covers. */
-#define SS_LOUD_SCRATCH_DOUBLES 16
+#define SS_LOUD_SCRATCH_DOUBLES 20
 typedef struct {
     const float* data;        /* element (n, c) at data[n * stride_n + c * stride_c]                   */
     float* out;               /* N*C contiguous floats = gain * data (may alias data); NULL = measure  */

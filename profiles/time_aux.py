@@ -41,7 +41,7 @@ stems = torch.randn((S, C, N), device=dev) * 0.05
 brk, blo, bhi = gating_plan(N, float(sr), 0.4)
 d_brk, d_lo, d_hi = (torch.from_numpy(a).to(dev) for a in (brk, blo, bhi))
 n_e = len(brk) - 1
-scr = torch.empty((S, _lib_scr := 16 * C * n_e), dtype=torch.float64, device=dev)
+scr = torch.empty((S, 20 * C * n_e), dtype=torch.float64, device=dev)          # SS_LOUD_SCRATCH_DOUBLES
 res = torch.empty((S, 2), dtype=torch.float64, device=dev)
 items = (_lib.SsLoudItem * S)()
 for i in range(S):

@@ -11,6 +11,7 @@ published algorithm because the package is not vendored in the reference: "parit
 """
 import ctypes
 import functools
+import os
 import math
 
 import numpy as np
@@ -21,11 +22,19 @@ from .dry import (create_background_audio, create_long_audio, get_random_wav_pat
 
 
 # ------------------------------------------------------------------------------------ loudness
+REFINE = int(os.environ.get("SS_LOUD_REFINE", "1"))     # elementary intervals per gating hop: more, shorter recurrences per
+                                                         # channel for the K-weighting kernels (experiment knob; measured: no gain,
+                                                         # the passes are bound by float64 throughput, not by thread count)
+
+
 @functools.lru_cache(maxsize=64)
-def gating_plan(num_samples: int, rate: float, block_size: float):
+def gating_plan(num_samples: int, rate: float, block_size: float, refine: int = REFINE):
     """Gating-block sample bounds exactly as pyloudnorm 0.1.1 computes them (meter.py: float
     expressions truncated with int(), 75 % overlap), in the compact form the C ABI takes:
-    (brk int32[n_e + 1], blk_lo int32[nb], blk_hi int32[nb])."""
+    (brk int32[n_e + 1], blk_lo int32[nb], blk_hi int32[nb]).  `brk` holds every distinct block bound plus
+    `refine - 1` evenly spaced cut points inside each interval between them: the kernels run one thread per
+    (channel, interval) and carry the exact filter state across intervals, so any partition gives the same result -
+    a finer one just means more, shorter threads."""
     T_g = block_size
     step = 1.0 - 0.75
     T = num_samples / rate
@@ -33,6 +42,10 @@ def gating_plan(num_samples: int, rate: float, block_size: float):
     lo = [min(int(T_g * (j * step) * rate), num_samples) for j in range(num_blocks)]
     hi = [min(int(T_g * (j * step + 1) * rate), num_samples) for j in range(num_blocks)]      # x[l:u] clips at N
     brk = np.unique(np.array(lo + hi, dtype=np.int64))
+    if refine > 1 and len(brk) > 1:
+        a, b = brk[:-1], brk[1:]
+        cuts = [a + (b - a) * k // refine for k in range(1, refine)]
+        brk = np.unique(np.concatenate([brk] + cuts))
     blk_lo = np.searchsorted(brk, lo).astype(np.int32)
     blk_hi = np.searchsorted(brk, hi).astype(np.int32)
     return brk.astype(np.int32), blk_lo, blk_hi

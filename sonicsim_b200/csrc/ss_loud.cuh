@@ -49,7 +49,7 @@ struct LoudItem {
     double inv_norm;         // 1 / (T_g * rate)
     double target;           // target LUFS (SonicSim_audio.py:77 `norm`)
 };
-constexpr int kLoudScratch = 16;   // doubles of scratch per (channel, elementary interval)
+constexpr int kLoudScratch = 20;   // doubles of scratch per (channel, elementary interval)
 
 // ---- K-weighting of one channel, EXACT and parallel over the elementary intervals.
 // pyloudnorm filters the whole channel with scipy.signal.lfilter (direct form II transposed, float64), stage by
@@ -57,8 +57,10 @@ constexpr int kLoudScratch = 16;   // doubles of scratch per (channel, elementar
 // interval e is   S_e = M^len(e-1) S_(e-1) + F_(e-1),   F = state at the end of an interval filtered from rest,
 // M = [[-a1, 1], [-a2, 0]].  Three passes, one thread per (channel, interval), each over its own samples only:
 //   pass 1  stage 1 from rest                                  -> F1, and M1^len, M2^len by repeated squaring
-//   pass 2  S1 by the recurrence over the earlier intervals; stage 1 exact, its float32 output through stage 2 from rest -> F2
-//   pass 3  S2 likewise; both stages exact; energy of the float32 output
+//   scan 1  S1 of every interval from (M1^len, F1): a scan over affine maps, one warp per channel on the device
+//   pass 2  stage 1 exact from S1, its float32 output through stage 2 from rest -> F2
+//   scan 2  S2 likewise
+//   pass 3  both stages exact; energy of the float32 output
 // No warm-up approximation: the result differs from lfilter's only by float64 rounding of the state recurrence.
 struct Mat2 { double a, b, c, d; };
 SS_HD Mat2 mat_mul(const Mat2& x, const Mat2& y) {
@@ -74,7 +76,7 @@ SS_HD Mat2 stage_matrix(const KCoef& k, int s) { Mat2 m; m.a = -k.a1[s]; m.b = 1
 
 // scratch slots of (channel c, interval e)
 SS_HD double* loud_slot(const LoudItem& it, int which, int c, int e) {
-    // which: 0 E(1) | 1 F1(2) | 2 S1(2) | 3 F2(2) | 4 M1(4) | 5 M2(4)
+    // which: 0 E(1) | 1 F1(2) | 2 S1(2) | 3 F2(2) | 4 M1(4) | 5 M2(4) | 6 S2(2)
     const long long ce = (long long)it.C * it.n_e, i = (long long)c * it.n_e + e;
     switch (which) {
         case 0: return it.E + i;
@@ -82,15 +84,19 @@ SS_HD double* loud_slot(const LoudItem& it, int which, int c, int e) {
         case 2: return it.E + 3 * ce + 2 * i;
         case 3: return it.E + 5 * ce + 2 * i;
         case 4: return it.E + 7 * ce + 4 * i;
-        default: return it.E + 11 * ce + 4 * i;
+        case 5: return it.E + 11 * ce + 4 * i;
+        default: return it.E + 15 * ce + 2 * i;
     }
 }
-// state at the start of interval e from the per-interval (M^len, F) of the intervals before it
-SS_HD void state_at(const LoudItem& it, int c, int e, int which_m, int which_f, double& z1, double& z2) {
-    z1 = 0; z2 = 0;
-    for (int q = 0; q < e; ++q) {
-        const double* m = loud_slot(it, which_m, c, q);
-        const double* f = loud_slot(it, which_f, c, q);
+// states at the start of every interval of channel c from the per-interval (M^len, F): the plain recurrence
+// (CPU emulation; k_kw_scan is the warp-parallel form).  stage 0: (M1, F1) -> S1, stage 1: (M2, F2) -> S2.
+SS_HD void kw_scan_serial(const LoudItem& it, int c, int stage) {
+    double z1 = 0, z2 = 0;
+    for (int e = 0; e < it.n_e; ++e) {
+        double* s = loud_slot(it, stage ? 6 : 2, c, e);
+        s[0] = z1; s[1] = z2;
+        const double* m = loud_slot(it, stage ? 5 : 4, c, e);
+        const double* f = loud_slot(it, stage ? 3 : 1, c, e);
         const double n1 = m[0] * z1 + m[1] * z2 + f[0], n2 = m[2] * z1 + m[3] * z2 + f[1];
         z1 = n1; z2 = n2;
     }
@@ -100,8 +106,8 @@ struct KwState { double z1a, z2a, z1b, z2b, acc; };
 template <int PASS>
 SS_HD void kw_begin(const LoudItem& it, int c, int e, KwState& st) {
     st.z1a = 0; st.z2a = 0; st.z1b = 0; st.z2b = 0; st.acc = 0;
-    if (PASS == 2) { state_at(it, c, e, 4, 1, st.z1a, st.z2a); double* s1 = loud_slot(it, 2, c, e); s1[0] = st.z1a; s1[1] = st.z2a; }
-    if (PASS == 3) { const double* s1 = loud_slot(it, 2, c, e); st.z1a = s1[0]; st.z2a = s1[1]; state_at(it, c, e, 5, 3, st.z1b, st.z2b); }
+    if (PASS >= 2) { const double* s1 = loud_slot(it, 2, c, e); st.z1a = s1[0]; st.z2a = s1[1]; }
+    if (PASS == 3) { const double* s2 = loud_slot(it, 6, c, e); st.z1b = s2[0]; st.z2b = s2[1]; }
 }
 template <int PASS>
 SS_HD void kw_sample(const KCoef& k, float xf, KwState& st) {

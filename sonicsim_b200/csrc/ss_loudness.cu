@@ -1,6 +1,7 @@
 // sonicsim_b200 :: ss_loudness.cu - SonicSim_audio.lufs_norm (SonicSim_audio.py:68-81) on the GPU.
-//   k_kweight<1,2,3> : one thread per (stem, channel, elementary interval); three passes over the thread's own interval
-//                      give the exact filter state at its start (ss_loud.cuh) and the energy of the K-weighted signal
+//   k_kweight<1,2,3> : one thread per (stem, channel, elementary interval); three passes over the thread's own interval,
+//   k_kw_scan          with a warp-parallel scan of the per-interval state maps between them, give the exact filter state at
+//                      every interval's start (ss_loud.cuh) and the energy of the K-weighted signal
 //   k_loud_gate      : one CTA per stem: block loudness, absolute / relative gates (fixed-order reductions), LUFS, gain
 //   k_loud_scale     : out = gain * data (float4 vectorised)
 #include <math.h>
@@ -69,6 +70,53 @@ k_kweight(const LoudItem* __restrict__ items, const int* __restrict__ prefix, in
         __syncwarp();
     }
     if (live) kw_end<PASS>(items[lo], k, c, e, st);
+}
+
+// States at the start of every interval of one (stem, channel): S_(e+1) = M_e S_e + F_e is a scan over affine maps
+// x -> A x + b.  One warp per (stem, channel): every lane composes the maps of its own run of intervals, the 32
+// composites are scanned with shuffles (composition is associative), then every lane walks its run again from the
+// state it starts in and stores the per-interval states.
+__global__ void __launch_bounds__(32) k_kw_scan(const LoudItem* __restrict__ items, int stage) {
+    const LoudItem& it = items[blockIdx.y];
+    const int c = blockIdx.x, lane = threadIdx.x;
+    if (c >= it.C) return;
+    const int wm = stage ? 5 : 4, wf = stage ? 3 : 1, ws = stage ? 6 : 2;
+    const int chunk = (it.n_e + 31) / 32;
+    const int e0 = lane * chunk < it.n_e ? lane * chunk : it.n_e, e1 = e0 + chunk < it.n_e ? e0 + chunk : it.n_e;
+    // composite of the lane's own run: x -> A x + b
+    double a00 = 1, a01 = 0, a10 = 0, a11 = 1, b0 = 0, b1 = 0;
+    for (int e = e0; e < e1; ++e) {
+        const double* m = loud_slot(it, wm, c, e);
+        const double* f = loud_slot(it, wf, c, e);
+        const double n00 = m[0] * a00 + m[1] * a10, n01 = m[0] * a01 + m[1] * a11;
+        const double n10 = m[2] * a00 + m[3] * a10, n11 = m[2] * a01 + m[3] * a11;
+        const double nb0 = m[0] * b0 + m[1] * b1 + f[0], nb1 = m[2] * b0 + m[3] * b1 + f[1];
+        a00 = n00; a01 = n01; a10 = n10; a11 = n11; b0 = nb0; b1 = nb1;
+    }
+    // inclusive scan over the lanes: (A, b) := (A, b) o (A', b') of the lane `o` below = (A A', A b' + b)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double p00 = __shfl_up_sync(0xffffffffu, a00, o), p01 = __shfl_up_sync(0xffffffffu, a01, o);
+        const double p10 = __shfl_up_sync(0xffffffffu, a10, o), p11 = __shfl_up_sync(0xffffffffu, a11, o);
+        const double q0 = __shfl_up_sync(0xffffffffu, b0, o), q1 = __shfl_up_sync(0xffffffffu, b1, o);
+        if (lane >= o) {
+            const double n00 = a00 * p00 + a01 * p10, n01 = a00 * p01 + a01 * p11;
+            const double n10 = a10 * p00 + a11 * p10, n11 = a10 * p01 + a11 * p11;
+            const double nb0 = a00 * q0 + a01 * q1 + b0, nb1 = a10 * q0 + a11 * q1 + b1;
+            a00 = n00; a01 = n01; a10 = n10; a11 = n11; b0 = nb0; b1 = nb1;
+        }
+    }
+    // state the lane's run starts in = what the maps of all lower lanes make of the rest state
+    double z1 = __shfl_up_sync(0xffffffffu, b0, 1), z2 = __shfl_up_sync(0xffffffffu, b1, 1);
+    if (lane == 0) { z1 = 0; z2 = 0; }
+    for (int e = e0; e < e1; ++e) {
+        double* s = loud_slot(it, ws, c, e);
+        s[0] = z1; s[1] = z2;
+        const double* m = loud_slot(it, wm, c, e);
+        const double* f = loud_slot(it, wf, c, e);
+        const double n1 = m[0] * z1 + m[1] * z2 + f[0], n2 = m[2] * z1 + m[3] * z2 + f[1];
+        z1 = n1; z2 = n2;
+    }
 }
 
 // Gating (pyloudnorm meter.py integrated_loudness; ss_loud.cuh loudness_gate is the one-thread statement of it that the
@@ -200,13 +248,16 @@ extern "C" int ss_loudness_dev(ss_ctx* c, const ss_loud_item* items, int n_items
     const LoudItem* d = (const LoudItem*)c->d_desc[slot];
     const int* dp = (const int*)(c->d_desc[slot] + off_p);
     const KCoef k = make_kcoef(items[0].rate);
+    const dim3 scan_grid(8, n_items);
     k_kweight<1><<<(tot + 127) / 128, 128, 0, stream>>>(d, dp, n_items, k);
+    k_kw_scan<<<scan_grid, 32, 0, stream>>>(d, 0);
     k_kweight<2><<<(tot + 127) / 128, 128, 0, stream>>>(d, dp, n_items, k);
+    k_kw_scan<<<scan_grid, 32, 0, stream>>>(d, 1);
     k_kweight<3><<<(tot + 127) / 128, 128, 0, stream>>>(d, dp, n_items, k);
     CK(cudaGetLastError());
     k_loud_gate<<<n_items, kGateThreads, 0, stream>>>(d, n_items);
     CK(cudaGetLastError());
-    c->launches += 4;
+    c->launches += 6;
     if (any_out) {
         dim3 grid(c->sm_count * 2, n_items);
         k_loud_scale<<<grid, 256, 0, stream>>>(d);

@@ -287,7 +287,9 @@ int emu_lufs(const float* data, int N, int C, long long stride_n, long long stri
     it.inv_norm = 1.0 / (block_size * rate); it.target = target;
     KCoef k = make_kcoef(rate);
     for (int c = 0; c < C; ++c) for (int e = 0; e < n_e; ++e) kweight_pass<1>(it, k, c, e);
+    for (int c = 0; c < C; ++c) kw_scan_serial(it, c, 0);
     for (int c = 0; c < C; ++c) for (int e = 0; e < n_e; ++e) kweight_pass<2>(it, k, c, e);
+    for (int c = 0; c < C; ++c) kw_scan_serial(it, c, 1);
     for (int c = 0; c < C; ++c) for (int e = 0; e < n_e; ++e) kweight_pass<3>(it, k, c, e);
     loudness_gate(it);
     return 0;
