@@ -33,8 +33,26 @@ constexpr int kPadF = kF + kF / 16;   // padded smem length in float2
 SS_HD int pad(int i) { return i + (i >> 4); }
 
 SS_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+#ifndef SS_PACKED_ADD
+#define SS_PACKED_ADD 1       // complex add / subtract as one packed fp32x2 instruction (sm_100 FADD2) instead of two FADD:
+                              // same IEEE result per lane, 260 fewer issue slots per thread and transform in k_render_fast
+                              // (117.2 -> 113.1 us; round 1 had measured the opposite on its 128-register kernel)
+#endif
+#if defined(__CUDA_ARCH__) && SS_PACKED_ADD
+SS_HD float2 cadd(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+SS_HD float2 csub(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+#else
 SS_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 SS_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 SS_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // a + w b, a - w b (4 FMA each) and 2 t - s (2 FMA): a twiddled radix-2 butterfly (t + w b, t - w b) costs
 // 6 instructions as (s = cfma(t, w, b), twice_minus(t, s)) instead of 8 as (cmul, cadd, csub).
@@ -92,6 +110,23 @@ SS_HD float lerp_terms(float fa, float a, float fb, float b) {
     return __fadd_rn(__fmul_rn(fa, a), __fmul_rn(fb, b));
 #else
     volatile float pa = fa * a, pb = fb * b;
+    return pa + pb;
+#endif
+}
+// (1 - w) * z.x + w * z.y, the same roundings as lerp_terms(1 - w, z.x, w, z.y); on the device the two products are one
+// packed multiply
+SS_HD float lerp_pair(float w, float2 z) {
+#if defined(__CUDA_ARCH__) && SS_PACKED_ADD
+    float2 f = make_float2(__fsub_rn(1.0f, w), w);
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&f)), "l"(*reinterpret_cast<unsigned long long*>(&z)));
+    const float2 p = *reinterpret_cast<float2*>(&r);
+    return __fadd_rn(p.x, p.y);
+#elif defined(__CUDA_ARCH__)
+    return __fadd_rn(__fmul_rn(__fsub_rn(1.0f, w), z.x), __fmul_rn(w, z.y));
+#else
+    volatile float omw = 1.0f - w;
+    volatile float pa = omw * z.x, pb = w * z.y;
     return pa + pb;
 #endif
 }

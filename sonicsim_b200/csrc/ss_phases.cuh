@@ -594,8 +594,7 @@ SS_HD void render_epilogue_item(int t, const RItem& it, const Regs32& R) {
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         const int n = nbase + 256 * r;
-        const float2 z = R.a[out16(r)];
-        const float v = lerp_terms(one_minus(w[r]), z.x, w[r], z.y);
+        const float v = lerp_pair(w[r], R.a[out16(r)]);
         if (n < n_end) row[n] = v;
     }
 }
