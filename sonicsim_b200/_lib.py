@@ -178,11 +178,16 @@ def check(status):
 _ctx = {}
 
 
+def default_device() -> int:
+    """CUDA ordinal the process renders on when none is given: SONICSIM_B200_DEVICE, else LOCAL_RANK, else 0."""
+    return int(os.environ.get("SONICSIM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
 def context(device=None):
     """One ss_ctx per (process, device).  Raises if no CUDA device is usable."""
     lib = load()
     if device is None:
-        device = int(os.environ.get("SONICSIM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        device = default_device()
     with _lock:
         if device in _ctx:
             return _ctx[device]

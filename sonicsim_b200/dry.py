@@ -138,9 +138,15 @@ def _assemble_device(raw, places, total: int, sample_rate: int, device):
     import ctypes
     import torch
     from . import _lib
-    from .render import default_renderer
-    R = default_renderer()
+    from .render import Renderer, default_renderer
     dev = torch.device(device)
+    if dev.type != "cuda":
+        raise ValueError("dry-stream assembly on a device needs a CUDA device, got %r" % (device,))
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    dev = torch.device("cuda", index)
+    R = default_renderer()
+    if R.device != index:                                         # a context of the library on the stream's own GPU
+        R = Renderer(index)
     out = torch.empty((1, total), dtype=torch.float32, device=dev)
     n = len(places)
     clips = (_lib.SsDryClip * max(n, 1))()

@@ -41,8 +41,8 @@ class Renderer:
 
     def __init__(self, device: T.Optional[int] = None):
         self.lib = _lib.load()
-        self.device = device
-        self.ctx = _lib.context(device)
+        self.device = _lib.default_device() if device is None else int(device)
+        self.ctx = _lib.context(self.device)
 
     # ------------------------------------------------------------------ host buffers
     def plan_host(self, sources: T.Sequence[T.Union[MovingSource, StaticSource]],
