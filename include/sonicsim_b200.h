@@ -95,6 +95,13 @@ int ss_set_chunk_bytes(ss_ctx* ctx, int64_t bytes);
  * non-decreasing with bounds[0] = 0 and bounds[P - 1] = N (anything else is undefined behaviour). */
 int ss_render_dev(ss_ctx* ctx, const ss_source* items, int n_items, void* stream);
 
+/* The device path cannot return SS_ERR_INDEX: kernels that meet a trajectory outside the contract above render the
+ * offending samples as silence (clamped positions) and set a bit that this call returns and clears after waiting for
+ * the device: bit 0 = an interp_index outside [0, P - 2], bit 1 = a device-side bounds table that is not ascending from
+ * 0 to N (checked for grid-blocked sources).  The Python device API raises IndexError / ValueError from it on request
+ * (Renderer.check_device_errors). */
+int ss_device_errors(ss_ctx* ctx, uint32_t* bits);
+
 /* A batch of device-resident sources bound once (the generation loop of SonicSet.py:180-214 renders the same
  * shapes scene after scene into the same buffers).  ss_plan_create validates, chunks, builds the block tables and
  * keeps the descriptor blocks and the scratch for the spectra resident; ss_plan_run is then kernel launches only,

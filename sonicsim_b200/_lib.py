@@ -117,6 +117,7 @@ def load():
         lib.ss_destroy.restype = None
         lib.ss_set_chunk_bytes.argtypes = [vp, i64]
         lib.ss_render_dev.argtypes = [vp, ctypes.POINTER(SsSource), ctypes.c_int, vp]
+        lib.ss_device_errors.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
         lib.ss_plan_create.argtypes = [vp, ctypes.POINTER(SsSource), ctypes.c_int, ctypes.POINTER(vp)]
         lib.ss_plan_run.argtypes = [vp, vp]
         lib.ss_plan_is_graph.argtypes = [vp]
@@ -154,7 +155,7 @@ def load():
 
 
 EXPORTS = ["ss_version", "ss_strerror", "ss_last_cuda_error", "ss_create", "ss_destroy",
-           "ss_set_chunk_bytes", "ss_render_dev", "ss_plan_create", "ss_plan_run", "ss_plan_is_graph", "ss_plan_destroy", "ss_render_host", "ss_render_host_ex", "ss_convolve_fixed_receiver",
+           "ss_set_chunk_bytes", "ss_render_dev", "ss_device_errors", "ss_plan_create", "ss_plan_run", "ss_plan_is_graph", "ss_plan_destroy", "ss_render_host", "ss_render_host_ex", "ss_convolve_fixed_receiver",
            "ss_convolve_moving_receiver", "ss_loudness_dev", "ss_lufs_norm_host", "ss_mix_scratch_doubles", "ss_mix_dev", "ss_mix_host",
            "ss_mix_host_ex", "ss_overlap_dev", "ss_overlap_host", "ss_dry_assemble_dev", "ss_debug_plan", "ss_debug_chunks", "ss_launch_count", "ss_reset_stats", "ss_set_profiling", "ss_get_profile", "ss_host_alloc",
            "ss_host_free"]

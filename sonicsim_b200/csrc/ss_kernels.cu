@@ -35,6 +35,11 @@
 
 using namespace ss;
 
+// Device-path trajectory check: the kernels cannot raise, so a source whose device-side trajectory breaks the contract
+// of ss_render_dev (idx outside [0, P - 2]; bounds not ascending from 0 to N) sets a bit here; ss_device_errors reads
+// and clears it.  bit 0: index out of range, bit 1: bounds not monotone / not ending at N.
+__device__ unsigned g_dev_err;
+
 // twiddle tables, filled from the host in double precision (ss_create)
 __device__ float2 g_tw[kF];          // exp(-2 pi i m / 8192)
 __device__ float2 g_twB[kTabB];      // [r][k] exp(-2 pi i k r / 256)
@@ -169,6 +174,11 @@ k_prepare(const Source* __restrict__ srcs_g, const int* __restrict__ prefix_g, i
         if (blk >= S.counts[0]) return;
         Block bk = S.blocks[blk];
         if (S.mode == MODE_MOVING_BOUNDS && !S.aligned) {
+            if (blk == 0 && lane == 0) {                   // one warp per source checks the device-side bounds table
+                bool bad = S.bounds[0] != 0 || S.bounds[S.P - 1] != S.N;
+                for (int q = 0; q + 1 < S.P && !bad; ++q) bad = S.bounds[q + 1] < S.bounds[q];
+                if (bad) atomicOr(&g_dev_err, 2u);
+            }
             bk.p_lo = seg_of(S.bounds, S.P - 1, bk.start);
             bk.p_hi = seg_of(S.bounds, S.P - 1, bk.start + bk.len - 1) + 1;
         } else if (S.mode == MODE_MOVING_INDEXED) {
@@ -179,7 +189,8 @@ k_prepare(const Source* __restrict__ srcs_g, const int* __restrict__ prefix_g, i
                 int a = __shfl_xor_sync(0xffffffffu, pmin, o), bm = __shfl_xor_sync(0xffffffffu, pmax, o);
                 pmin = a < pmin ? a : pmin; pmax = bm > pmax ? bm : pmax;
             }
-            // the reference raises IndexError for idx + 1 >= P (checked on the host path); clamp here
+            // the reference raises IndexError for idx + 1 >= P (checked on the host path); clamp here, leave a mark
+            if (lane == 0 && (pmin < 0 || pmax + 1 > S.P - 1)) atomicOr(&g_dev_err, 1u);
             bk.p_lo = pmin < 0 ? 0 : pmin;
             bk.p_hi = pmax + 1 > S.P - 1 ? S.P - 1 : pmax + 1;
         }
@@ -691,6 +702,7 @@ static int init_ctx(ss_ctx* c, int device) {
     }
     CK(cudaMemcpyToSymbol(g_twB, tb.data(), sizeof(float2) * kTabB));
     CK(cudaMemcpyToSymbol(g_twC, tc.data(), sizeof(float2) * kTabC));
+    { const unsigned zero = 0; CK(cudaMemcpyToSymbol(g_dev_err, &zero, sizeof(zero))); }
     CK(cudaFuncSetAttribute(k_prepare<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
     CK(cudaFuncSetAttribute(k_prepare<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
     CK(cudaFuncSetAttribute(k_render<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmem));
@@ -758,6 +770,18 @@ extern "C" void ss_destroy(ss_ctx* c) {
     if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     delete c;
+}
+
+// Bits set by the kernels of this context's device since the last call (waits for the device to go idle).
+extern "C" int ss_device_errors(ss_ctx* c, uint32_t* bits) {
+    if (!c || !bits) return SS_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    unsigned v = 0, zero = 0;
+    CK(cudaMemcpyFromSymbol(&v, g_dev_err, sizeof(v)));
+    if (v) CK(cudaMemcpyToSymbol(g_dev_err, &zero, sizeof(zero)));
+    *bits = v;
+    return SS_OK;
 }
 
 extern "C" int ss_set_chunk_bytes(ss_ctx* c, int64_t bytes) {

@@ -176,6 +176,17 @@ class Renderer:
                                     flags=_lib.SS_RIR_NORMALIZE if s.normalize_rirs else 0)
         return items, n, keep
 
+    def check_device_errors(self):
+        """Waits for the device and raises what the reference would have raised for a trajectory the device path met
+        but could not refuse up front: IndexError for an interp_index outside [0, P - 2] (NumPy's fancy index at
+        SonicSim_moving.py:89-90), ValueError for a device-side bounds table that is not ascending from 0 to N."""
+        bits = ctypes.c_uint32()
+        _lib.check(self.lib.ss_device_errors(self.ctx, ctypes.byref(bits)))
+        if bits.value & 1:
+            raise IndexError("an interp_index on the device was out of bounds for the number of RIR positions")
+        if bits.value & 2:
+            raise ValueError("a device-side trajectory bounds table is not ascending from 0 to N")
+
     def launch_count(self) -> int:
         return int(self.lib.ss_launch_count(self.ctx))
 

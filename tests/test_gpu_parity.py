@@ -339,3 +339,42 @@ def test_device_plan_is_one_graph_launch_and_matches_direct_launches():
             R.plan_device([render.MovingSource(dev[0].dry.cpu(), dev[0].rirs, dev[0].bounds)], [outs[0]])
     finally:
         R.set_chunk_bytes(96 << 20)
+
+
+def test_device_path_reports_trajectories_it_cannot_refuse():
+    """ss_render_dev takes device pointers and cannot check idx / bounds up front like the host path does (IndexError /
+    ValueError there).  Kernels that meet an out-of-contract trajectory clamp, and set a flag that
+    Renderer.check_device_errors turns into the reference's exception types."""
+    import ctypes
+    from sonicsim_b200 import _lib, render
+    R = render.default_renderer()
+    R.check_device_errors()                               # clean so far
+    rng = np.random.default_rng(8)
+    P, C, L, N = 5, 2, 300, 20000
+    x, h = torch.from_numpy(so.synth_dry(rng, N)).cuda(), torch.from_numpy(so.synth_rirs(rng, P, C, L)).cuda()
+    out = torch.empty((C, N), device="cuda")
+    idx = torch.randint(0, P - 1, (N,), dtype=torch.int32, device="cuda")
+    w = torch.rand(N, device="cuda")
+    item = (_lib.SsSource * 1)(_lib.SsSource(x=x.data_ptr(), rir=h.data_ptr(), out=out.data_ptr(), idx=idx.data_ptr(), w=w.data_ptr(),
+                                             N=N, P=P, C=C, L=L, mode=_lib.SS_MOVING_INDEXED))
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(R.lib.ss_render_dev(R.ctx, item, 1, stream))
+    R.check_device_errors()                               # valid indices: nothing to report
+    ref = so.convolve_moving_receiver(x.cpu().numpy(), h.cpu().numpy(), idx.cpu().numpy().astype(np.int64), w.cpu().numpy())
+    assert so.rel_rms(out.cpu().numpy(), ref) < TOL
+    idx[N // 2] = P - 1                                   # idx + 1 == P: the reference raises IndexError
+    _lib.check(R.lib.ss_render_dev(R.ctx, item, 1, stream))
+    with pytest.raises(IndexError):
+        R.check_device_errors()
+    R.check_device_errors()                               # the flag is cleared by reading it
+    # device-only bounds table that does not end at N (many short segments -> grid blocking, where it is checked)
+    P2 = 20
+    h2 = torch.from_numpy(so.synth_rirs(rng, P2, C, L)).cuda()
+    bounds = torch.linspace(0, N, P2).to(torch.int32).cuda()
+    out2 = [torch.empty((C, N), device="cuda")]
+    R.render_device([render.MovingSource(x, h2, bounds)], out2)
+    R.check_device_errors()
+    bounds[-1] = N - 5
+    R.render_device([render.MovingSource(x, h2, bounds)], out2)
+    with pytest.raises(ValueError):
+        R.check_device_errors()
