@@ -38,7 +38,6 @@ struct ss_ctx {
     int64_t launches = 0;
     bool single_stream = false;   // experiment knob (SS_SINGLE_STREAM=1): no chunk overlap
     bool no_fast = false;         // experiment knob (SS_NO_FAST=1): never pick the all-aligned kernel variant
-    const float2* d_ones = nullptr;   // device address of the unit-impulse spectrum (k_zmac path)
     bool no_graph = false;        // experiment knob (SS_NO_GRAPH=1): plans enqueue their launches instead of a CUDA graph
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profiling = false;

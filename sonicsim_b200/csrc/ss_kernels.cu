@@ -40,8 +40,6 @@ using namespace ss;
 // and clears it.  bit 0: index out of range, bit 1: bounds not monotone / not ending at N.
 __device__ unsigned g_dev_err;
 
-__device__ float2 g_ones[kSpec];     // half spectrum of a unit impulse: [0] = (DC, Nyquist) = (1, 1), every other bin 1 + 0 i
-
 // twiddle tables, filled from the host in double precision (ss_create)
 __device__ float2 g_tw[kF];          // exp(-2 pi i m / 8192)
 __device__ float2 g_twB[kTabB];      // [r][k] exp(-2 pi i k r / 256)
@@ -153,65 +151,6 @@ struct PrepParams {
     Source srcs[kPrepInline];
 };
 static_assert(sizeof(PrepParams) <= 4000, "kernel parameter space");
-
-// ----------------------------------------------------------------------------- k_zmac
-// Long RIRs (K = ceil(L / 4096) > 1 partitions): Z[b, c, p] = sum_j X[b - j] H[p, c, j] for every block b, channel c
-// and position p the block needs.  k_render<LONG> stages three spectra per partition and transform (96 KB from L2 each,
-// ~10 TB/s at configs[3]); here the sum is formed once per (position, run of blocks that need it): a thread owns one
-// frequency bin, keeps the accumulators of up to kZG blocks x kZC channels in registers, and walks the partitions with a
-// sliding window over the dry spectra, so every filter spectrum is read once per run instead of once per block.
-// k_render then runs its single-partition path on the accumulated spectra (dry spectrum = that of a unit impulse).
-constexpr int kZG = 8, kZC = 4;
-template <bool DCNY>
-__device__ __forceinline__ void zmac(float2& acc, float2 x, float2 h) {
-    if (DCNY) { acc.x = fmaf(x.x, h.x, acc.x); acc.y = fmaf(x.y, h.y, acc.y); }       // packed (DC, Nyquist) word: two real products
-    else cmac(acc, x, h);
-}
-template <bool DCNY>
-__device__ __forceinline__ void zmac_run(const Source& S, const ZRun& r, int k, int c0) {
-    float2 acc[kZG][kZC], xs[kZG];
-#pragma unroll
-    for (int i = 0; i < kZG; ++i) {
-#pragma unroll
-        for (int cc = 0; cc < kZC; ++cc) acc[i][cc] = make_float2(0.f, 0.f);
-        xs[i] = i < r.g ? S.xspec[(size_t)(r.b0 + i) * kSpec + k] : make_float2(0.f, 0.f);
-    }
-    const int nc = S.C - c0 < kZC ? S.C - c0 : kZC;
-    const int jmax = r.b0 + r.g < S.K ? r.b0 + r.g : S.K;          // partitions that reach back into the signal for some block
-    for (int j = 0; j < jmax; ++j) {
-        float2 hv[kZC];
-#pragma unroll
-        for (int cc = 0; cc < kZC; ++cc)
-            hv[cc] = cc < nc ? S.hspec[(((size_t)r.p * S.C + c0 + cc) * S.K + j) * kSpec + k] : make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < kZG; ++i)
-#pragma unroll
-            for (int cc = 0; cc < kZC; ++cc) zmac<DCNY>(acc[i][cc], xs[i], hv[cc]);
-        // window of the next partition: block b0 + i pairs with the dry window one block earlier
-#pragma unroll
-        for (int i = kZG - 1; i > 0; --i) xs[i] = xs[i - 1];
-        const int bn = r.b0 - (j + 1);
-        xs[0] = bn >= 0 ? S.xspec[(size_t)bn * kSpec + k] : make_float2(0.f, 0.f);
-    }
-#pragma unroll
-    for (int i = 0; i < kZG; ++i) {
-        if (i < r.g) {
-            const ZBlk zb = S.zblk[r.b0 + i];
-            float2* dst = S.zspec + ((size_t)zb.zoff * S.C + (size_t)c0 * zb.npos + (r.p - zb.p_lo)) * kSpec + k;
-#pragma unroll
-            for (int cc = 0; cc < kZC; ++cc) if (cc < nc) dst[(size_t)cc * zb.npos * kSpec] = acc[i][cc];
-        }
-    }
-}
-__global__ void __launch_bounds__(256)
-k_zmac(const Source* __restrict__ srcs, const ZRun* __restrict__ runs) {
-    const ZRun r = runs[blockIdx.x];
-    const Source& S = srcs[r.src];
-    const int c0 = blockIdx.z * kZC;
-    if (c0 >= S.C) return;
-    const int k = blockIdx.y * 256 + threadIdx.x;
-    if (k == 0) zmac_run<true>(S, r, k, c0); else zmac_run<false>(S, r, k, c0);
-}
 
 #ifndef SS_PREP_MINB
 #define SS_PREP_MINB 2        // resident CTAs per SM the register allocation of k_prepare aims at (3 fits shared memory)
@@ -720,7 +659,6 @@ k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_p
 
 // ============================================================================= host side
 thread_local int g_last_cuda = 0;
-static bool g_no_zmac = false;                          // experiment knob SS_NO_ZMAC=1 (read in init_ctx): long RIRs stay on k_render<LONG>
 
 extern "C" int ss_version(void) { return 100; }
 extern "C" int ss_last_cuda_error(void) { return g_last_cuda; }
@@ -764,11 +702,6 @@ static int init_ctx(ss_ctx* c, int device) {
     }
     CK(cudaMemcpyToSymbol(g_twB, tb.data(), sizeof(float2) * kTabB));
     CK(cudaMemcpyToSymbol(g_twC, tc.data(), sizeof(float2) * kTabC));
-    {
-        std::vector<float2> ones(kSpec, make_float2(1.f, 0.f));
-        ones[0] = make_float2(1.f, 1.f);
-        CK(cudaMemcpyToSymbol(g_ones, ones.data(), sizeof(float2) * kSpec));
-    }
     { const unsigned zero = 0; CK(cudaMemcpyToSymbol(g_dev_err, &zero, sizeof(zero))); }
     CK(cudaFuncSetAttribute(k_prepare<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
     CK(cudaFuncSetAttribute(k_prepare<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadF * (int)sizeof(float2)));
@@ -793,8 +726,6 @@ static int init_ctx(ss_ctx* c, int device) {
     c->single_stream = getenv("SS_SINGLE_STREAM") != nullptr;
     c->no_fast = getenv("SS_NO_FAST") != nullptr;
     c->no_graph = getenv("SS_NO_GRAPH") != nullptr;
-    g_no_zmac = getenv("SS_NO_ZMAC") != nullptr;
-    { void* p_ones = nullptr; CK(cudaGetSymbolAddress(&p_ones, g_ones)); c->d_ones = (const float2*)p_ones; }
     if (getenv("SS_HOST_CHUNK_MB")) c->chunk_bytes_host = (int64_t)atoi(getenv("SS_HOST_CHUNK_MB")) << 20;
     return SS_OK;
 }
@@ -952,49 +883,8 @@ static Shape shape_of(const ss_source& it) {
     s.max_items = s.nblk_max * s.per;
     return s;
 }
-// ---- k_zmac planning (host): long-RIR sources whose trajectory is visible on the host
-static bool zmac_eligible(const ss_source& it, const Shape& sh) {
-    return !g_no_zmac && sh.K > 1 && it.mode == SS_MOVING_BOUNDS && it.bounds_host != nullptr;
-}
-// positions every 4096-grid block needs (as k_prepare's range CTAs compute them with seg_of); returns their total
-static int64_t zmac_layout(const ss_source& it, const Shape& sh, ZBlk* zb) {
-    int64_t tot = 0;
-    for (int b = 0; b < sh.nb; ++b) {
-        const int start = b * kB, len = it.N - start < kB ? it.N - start : kB;
-        const int p_lo = seg_of(it.bounds_host, it.P - 1, start);
-        const int p_hi = seg_of(it.bounds_host, it.P - 1, start + len - 1) + 1;
-        if (zb) { zb[b].zoff = (int)tot; zb[b].p_lo = p_lo; zb[b].npos = p_hi - p_lo + 1; zb[b].pad_ = 0; }
-        tot += p_hi - p_lo + 1;
-    }
-    return tot;
-}
-// runs of blocks per position, cut into pieces of at most kZG blocks; appends to `out` (may be null: count only)
-static int zmac_runs(const ss_source& it, const Shape& sh, int src, std::vector<ZRun>* out) {
-    std::vector<int> first((size_t)it.P, -1), last((size_t)it.P, -1);
-    for (int b = 0; b < sh.nb; ++b) {
-        const int start = b * kB, len = it.N - start < kB ? it.N - start : kB;
-        const int p_lo = seg_of(it.bounds_host, it.P - 1, start);
-        const int p_hi = seg_of(it.bounds_host, it.P - 1, start + len - 1) + 1;
-        for (int p = p_lo; p <= p_hi; ++p) { if (first[p] < 0) first[p] = b; last[p] = b; }
-    }
-    int n = 0;
-    for (int p = 0; p < it.P; ++p) {
-        if (first[p] < 0) continue;
-        for (int b0 = first[p]; b0 <= last[p]; b0 += kZG) {
-            if (out) { ZRun r; r.src = src; r.p = p; r.b0 = b0; r.g = last[p] - b0 + 1 < kZG ? last[p] - b0 + 1 : kZG; out->push_back(r); }
-            ++n;
-        }
-    }
-    return n;
-}
-
 static size_t spectra_bytes(const ss_source& it) {
     const Shape sh = shape_of(it);
-    if (zmac_eligible(it, sh))
-        return ((size_t)it.P * it.C * sh.K + sh.nblk_max) * kSpec * sizeof(float2) + (size_t)sh.max_items * sizeof(RItem) +
-               align_up(sizeof(Block) * (size_t)sh.nblk_max, 256) + align_up(sizeof(double) * (size_t)it.P, 256) + 256 +
-               ((it.flags & SS_RIR_NORMALIZE) ? 512 : 0) +
-               (size_t)zmac_layout(it, sh, nullptr) * it.C * kSpec * sizeof(float2) + 256;
     return ((size_t)it.P * it.C * sh.K + sh.nblk_max) * kSpec * sizeof(float2) + (size_t)sh.max_items * sizeof(RItem) +
            align_up(sizeof(Block) * (size_t)sh.nblk_max, 256) + align_up(sizeof(double) * (size_t)it.P, 256) + 256 +
            ((it.flags & SS_RIR_NORMALIZE) ? 512 : 0);
@@ -1049,8 +939,7 @@ extern "C" int ss_debug_plan(const ss_source* item, int32_t* blocks_out, int32_t
 // Everything the launches need besides the descriptor block in device memory.
 struct ChunkLaunch {
     int n = 0, ps = 0, grid_r = 0, n_known = -1;
-    bool host_tables = true, any_long = false, all_aligned = true, any_norm = false, zmac = false;
-    const ZRun* d_runs = nullptr; int n_runs = 0, zc = 1;
+    bool host_tables = true, any_long = false, all_aligned = true, any_norm = false;
     const Source* ds = nullptr; const int* dps = nullptr; RItem* d_items = nullptr; int* d_total = nullptr;
     PrepParams pp;
 };
@@ -1065,12 +954,7 @@ static bool chunk_host_tables(const ss_source* items, int first, int last) {
         if (items[i].mode == SS_MOVING_BOUNDS && !items[i].bounds_host) return false;
     return true;
 }
-// every source of the chunk is a long-RIR source that k_zmac can plan on the host
-static bool chunk_zmac(const ss_source* items, int first, int last) {
-    for (int i = first; i < last; ++i) if (!zmac_eligible(items[i], shape_of(items[i]))) return false;
-    return last > first;
-}
-// descriptor block: Source[n] | prefix_prepare[n+1] | total | per source: blocks, rstep, counts [| ZBlk] [| ZRun of the chunk]
+// descriptor block: Source[n] | prefix_prepare[n+1] | total | per source: blocks, rstep, counts
 static size_t chunk_desc_bytes(const ss_source* items, int first, int last) {
     const int n = last - first;
     size_t bytes = align_up(sizeof(Source) * n, 16) + align_up(sizeof(int) * (n + 1), 16) + 16;
@@ -1079,26 +963,14 @@ static size_t chunk_desc_bytes(const ss_source* items, int first, int last) {
             const Shape sh = shape_of(items[i]);
             bytes += align_up(sizeof(Block) * (size_t)sh.nblk_max, 16) + align_up(sizeof(double) * (size_t)items[i].P, 16) + 16;
         }
-    if (chunk_zmac(items, first, last)) {
-        size_t n_runs = 0;
-        for (int i = first; i < last; ++i) {
-            const Shape sh = shape_of(items[i]);
-            bytes += align_up(sizeof(ZBlk) * (size_t)sh.nb, 16);
-            n_runs += (size_t)zmac_runs(items[i], sh, 0, nullptr);
-        }
-        bytes += align_up(sizeof(ZRun) * n_runs, 16);
-    }
     return bytes;
 }
 // Fill the descriptor block of items[first, last) at `hbase` (host memory) for its device address `dbase`, carve the
 // chunk's spectra / tables / work items out of `scratch` (device), and note the launch parameters in `L`.
 static void chunk_describe(const ss_source* items, int first, int last, char* hbase, char* dbase, char* scratch,
-                           int sm_count, const float2* d_ones, ChunkLaunch* L) {
+                           int sm_count, ChunkLaunch* L) {
     const int n = last - first;
     const bool host_tables = chunk_host_tables(items, first, last);
-    const bool zm = chunk_zmac(items, first, last);
-    std::vector<ZRun> runs;
-    int zc = 1;
     const size_t off_ps = align_up(sizeof(Source) * n, 16);
     const size_t off_tot = off_ps + align_up(sizeof(int) * (n + 1), 16);
     Source* hs = (Source*)hbase;
@@ -1131,15 +1003,6 @@ static void chunk_describe(const ss_source* items, int first, int last, char* hb
             const int nblk = build_blocks_host(it, sh, it.bounds_host, hb_blocks, hb_rstep);
             hb_counts[0] = nblk; hb_counts[1] = total_items; hb_counts[2] = 0; hb_counts[3] = 0;
             total_items += nblk * sh.per;
-            if (zm) {
-                ZBlk* hb_z = (ZBlk*)(hbase + tab_off);
-                s.zblk = (const ZBlk*)(dbase + tab_off); tab_off += align_up(sizeof(ZBlk) * (size_t)sh.nb, 16);
-                const int64_t tot = zmac_layout(it, sh, hb_z);
-                s.zspec = (float2*)scratch; scratch += (size_t)tot * s.C * kSpec * sizeof(float2) + 256;
-                s.ones = d_ones;
-                zmac_runs(it, sh, i, &runs);
-                if ((s.C + kZC - 1) / kZC > zc) zc = (s.C + kZC - 1) / kZC;
-            }
         } else {
             s.blocks = (Block*)scratch; scratch += align_up(sizeof(Block) * (size_t)s.nblk_max, 256);
             s.rstep = (double*)scratch; scratch += align_up(sizeof(double) * (size_t)s.P, 256);
@@ -1152,12 +1015,6 @@ static void chunk_describe(const ss_source* items, int first, int last, char* hb
         any_long = any_long || s.K > 1; all_aligned = all_aligned && s.aligned;
     }
     hps[n] = ps;
-    L->zmac = zm; L->n_runs = (int)runs.size(); L->zc = zc; L->d_runs = nullptr;
-    if (zm) {
-        memcpy(hbase + tab_off, runs.data(), sizeof(ZRun) * runs.size());
-        L->d_runs = (const ZRun*)(dbase + tab_off); tab_off += align_up(sizeof(ZRun) * runs.size(), 16);
-        any_long = false;                                 // k_render sees single-partition items
-    }
     // work-item table of the whole chunk (dense) + its length
     L->d_items = (RItem*)scratch; scratch += (size_t)pr * sizeof(RItem);
     L->d_total = host_tables ? (int*)(dbase + off_tot) : (int*)scratch;
@@ -1193,11 +1050,6 @@ static int chunk_enqueue(ss_ctx* c, const ChunkLaunch& L, cudaStream_t stream, s
         CK(cudaGetLastError());
     }
     if (pf) CK(cudaEventRecord(pf->e1, stream));
-    if (L.zmac && L.n_runs > 0) {
-        k_zmac<<<dim3((unsigned)L.n_runs, kSpec / 256, (unsigned)L.zc), 256, 0, stream>>>(L.ds, L.d_runs);
-        CK(cudaGetLastError());
-        c->launches += 1;
-    }
     if (L.grid_r > 0) {
         if (L.any_long) k_render<true, false><<<L.grid_r, kThreads, kRenderSmem, stream>>>(L.d_items, L.d_total, L.n_known);
         else if (L.all_aligned && !c->no_fast) k_render_fast<<<L.grid_r, kThreads, kRenderSmem, stream>>>(L.d_items, L.d_total, L.n_known);
@@ -1225,7 +1077,7 @@ static int launch_chunk(ss_ctx* c, const ss_source* items, int first, int last, 
     int slot; char *hblk, *dblk;
     { int st = ring_acquire(c, bytes, &slot, &hblk, &dblk); if (st) return st; }
     static thread_local ChunkLaunch L;                  // holds 3.2 KB of kernel parameters: not on the stack
-    chunk_describe(items, first, last, hblk, dblk, c->d_scratch[buf], c->sm_count, c->d_ones, &L);
+    chunk_describe(items, first, last, hblk, dblk, c->d_scratch[buf], c->sm_count, &L);
     CK(cudaMemcpyAsync(dblk, hblk, bytes, cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(c->desc_ev[slot], stream));
     ss_ctx::Prof pf;
@@ -1390,8 +1242,8 @@ static int plan_build(ss_plan* p, const ss_source* items, int n_items) {
     p->launches_per_run = 0;
     for (size_t k = 0; k < n_chunks; ++k) {
         chunk_describe(items, cuts[k], cuts[k + 1], host.data() + off[k], p->d_desc + off[k],
-                       p->d_scratch[n_chunks < 2 ? 0 : k % ss_ctx::kAux], c->sm_count, c->d_ones, &p->chunks[k]);
-        p->launches_per_run += (p->chunks[k].host_tables ? 2 : 3) + (p->chunks[k].any_norm ? 1 : 0) + (p->chunks[k].zmac ? 1 : 0);
+                       p->d_scratch[n_chunks < 2 ? 0 : k % ss_ctx::kAux], c->sm_count, &p->chunks[k]);
+        p->launches_per_run += (p->chunks[k].host_tables ? 2 : 3) + (p->chunks[k].any_norm ? 1 : 0);
     }
     CK(cudaMemcpy(p->d_desc, host.data(), off[n_chunks], cudaMemcpyHostToDevice));
     return SS_OK;

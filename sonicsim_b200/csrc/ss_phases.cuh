@@ -20,11 +20,6 @@ enum { MODE_STATIC = 0, MODE_MOVING_BOUNDS = 1, MODE_MOVING_INDEXED = 2 };
 struct Block { int start, len, p_lo, p_hi; };
 
 struct RItem;
-// k_zmac's view of one block of a long-RIR source: spectra of positions p_lo .. p_lo + npos - 1 for channel c live at
-// zspec + ((zoff * C + c * npos) + (p - p_lo)) * kSpec
-struct ZBlk { int zoff, p_lo, npos, pad_; };
-// one unit of k_zmac work: position p of source src for the run of blocks b0 .. b0 + g - 1 that need it
-struct ZRun { int src, p, b0, g; };
 
 // One (utterance, source) unit.  Reference shapes: dry (N,), RIRs (P, C, L), output (C, N)
 // (SonicSim_moving.py:63-96); static source has P = 1 (SonicSim_moving.py:47-61).
@@ -41,10 +36,6 @@ struct Source {
     double* rstep;         // scratch: 1 / (samples in segment s), s < P - 1 (mode 1)
     int* counts;           // scratch: [0] = blocks in use, [1] = index of this source's first render item
     const float* norm_part;// scratch: kNormParts partial abs-maxima of the RIR tensor (k_rir_absmax), or null: taps used as given
-    float2* zspec;         // scratch (long RIRs, k_zmac): per block, channel and position the accumulated product spectrum
-                           // sum_j X[b - j] H[p, c, j]; null: k_render accumulates the partitions itself
-    const ZBlk* zblk;      // per block: where its spectra start in zspec, first position, number of positions
-    const float2* ones;    // the half spectrum of a unit impulse (what k_render multiplies the accumulated spectra with)
     int N, P, C, L;
     int K;                 // RIR partitions = ceil(L / kB)
     int nb;                // ceil(N / kB)
@@ -119,22 +110,6 @@ SS_HD void fill_items(const Source& s, RItem* items, int blk, const Block& bk, i
     if (s.aligned) { it.b0 = s.bounds[bk.p_lo]; it.step = s.rstep[bk.p_lo]; }
     const int per = items_per_block(s);
     RItem* dst = items + s.counts[1] + (size_t)blk * per;
-    if (s.zspec) {
-        // long RIR, spectra already accumulated over the partitions by k_zmac: one "partition" whose filters are the
-        // accumulated spectra (position p at H0 + p * kSpec) and whose dry spectrum is that of a unit impulse
-        const ZBlk zb = s.zblk[blk];
-        it.X = s.ones;
-        it.kparts = 1;
-        for (int c = lane; c < per; c += nlanes) {
-            it.H0 = s.zspec + ((size_t)zb.zoff * s.C + (size_t)c * zb.npos) * kSpec - (size_t)zb.p_lo * kSpec;
-            it.row = s.out + (size_t)c * s.N;
-            it.row1 = nullptr;
-            it.pstride = kSpec;
-            it.p_lo = zb.p_lo; it.p_hi = zb.p_lo + zb.npos - 1;
-            dst[c] = it;
-        }
-        return;
-    }
     if (s.mode == MODE_STATIC) {
         for (int cp = lane; cp < per; cp += nlanes) {
             it.H0 = s.hspec + (size_t)(2 * cp) * s.K * kSpec;

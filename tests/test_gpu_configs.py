@@ -109,11 +109,10 @@ def test_cfg5_binaural_dual_render():
     assert so.rel_rms(outs[3], so.convolve_fixed_receiver(music[None], hm)) < TOL
 
 
-def test_long_rir_frequency_domain_accumulation_kernel():
-    """Long RIRs with a host-visible trajectory go through k_zmac (sum over the RIR partitions formed once per position
-    and run of blocks) + the single-partition render; the (idx, w) form of the same render still accumulates inside
-    k_render<LONG>.  Both against the oracle and against each other; 5 channels = two channel groups of k_zmac; many
-    short segments = blocks that need three and more positions; device plan == host path bit for bit."""
+def test_long_rir_compact_trajectory_vs_indexed_and_device_plan():
+    """Long RIRs (several partitions accumulated in the frequency domain): the compact-trajectory form and the (idx, w)
+    form of the same render against the oracle and against each other; 5 channels, many short segments (blocks that need
+    three and more positions), L just above one partition; the device plan equals the host path bit for bit."""
     import torch
     from sonicsim_b200 import SonicSim_moving as sm, render
     R = render.default_renderer()
@@ -124,8 +123,8 @@ def test_long_rir_frequency_domain_accumulation_kernel():
         idx, w = so.setup_dynamic_interp(pos, N)
         bounds = np.concatenate([[0], np.cumsum(np.bincount(idx, minlength=P - 1))]).astype(np.int32)
         ref = so.convolve_moving_receiver(x, h, idx, w)
-        y_b = R.render_host([render.MovingSource(x, h, bounds)])[0]            # k_zmac + k_render<0, 0>
-        y_i = sm.convolve_moving_receiver(x, h, idx, w)                         # k_render<1, 0>
+        y_b = R.render_host([render.MovingSource(x, h, bounds)])[0]
+        y_i = sm.convolve_moving_receiver(x, h, idx, w)
         assert so.rel_rms(y_b, ref) < TOL and so.rel_rms(y_i, ref) < TOL
         assert so.rel_rms(y_b, y_i) < 2e-6
         dev = [render.MovingSource(torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda(), torch.from_numpy(bounds).cuda(), bounds)]
