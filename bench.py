@@ -406,7 +406,7 @@ def run_ours(args, rank, local_rank, world):
             shape = (CFG["P"], CFG["C"], CFG["L"], CFG["N"])
             t1 = cpu_bench.single_thread_time(shape, reps=1)
             pool = cpu_bench.CpuPool(shape=shape)
-            cal = pool.calibrate(budget_s=36.0)          # bounded sample: full batches at cores, cores / 2, ...
+            cal = pool.calibrate(budget_s=48.0)          # bounded sample: full batches at cores, cores / 2, ...
             w_use, t = cal[0]
             kind = pool.kind
             pool.close()
