@@ -1123,6 +1123,27 @@ static void make_chunks(const ss_ctx* c, const ss_source* items, int n, std::vec
     for (int i = 0; i < n; ++i) sb[i] = spectra_bytes(items[i]);
     make_chunks_bytes(sb, budget, cuts);
 }
+// Device path: sources are independent, so a batch is regrouped by the kernel variant its chunk would run - sources
+// under aligned blocking (k_render_fast), long RIRs (k_render<LONG>), everything else (k_render<0, 0>) - and each group
+// is chunked on its own: one static source no longer sends the moving sources of its chunk through the generic kernel
+// (a SonicSet scene is 3 moving + 2 static sources).  `arranged` receives the regrouped items, `cuts` the chunk bounds.
+static void arrange_chunks(const ss_ctx* c, const ss_source* items, int n, std::vector<ss_source>& arranged, std::vector<int>& cuts) {
+    arranged.clear(); arranged.reserve(n);
+    cuts.clear(); cuts.push_back(0);
+    for (int cls = 0; cls < 3; ++cls) {
+        const int lo = (int)arranged.size();
+        for (int i = 0; i < n; ++i) {
+            const Shape sh = shape_of(items[i]);
+            const int k = sh.K > 1 ? 1 : (sh.aligned ? 0 : 2);
+            if (k == cls) arranged.push_back(items[i]);
+        }
+        const int cnt = (int)arranged.size() - lo;
+        if (cnt == 0) continue;
+        std::vector<int> local;
+        make_chunks(c, arranged.data() + lo, cnt, local);
+        for (size_t q = 1; q < local.size(); ++q) cuts.push_back(lo + local[q]);
+    }
+}
 // Test hook (pure host): the chunking of items whose scratch needs are `bytes[i]` under `budget`; cuts_out receives
 // the first item of every chunk plus n (at most max_cuts values); returns the number of values written or a negative status.
 extern "C" int ss_debug_chunks(const int64_t* bytes, int32_t n, int64_t budget, int32_t* cuts_out, int32_t max_cuts) {
@@ -1154,7 +1175,9 @@ extern "C" int ss_render_dev(ss_ctx* c, const ss_source* items, int n_items, voi
     CK(cudaSetDevice(c->device));
     { int st = validate_dev_items(items, n_items); if (st) return st; }
     std::vector<int> cuts;
-    make_chunks(c, items, n_items, cuts);
+    std::vector<ss_source> arranged;
+    arrange_chunks(c, items, n_items, arranged, cuts);
+    items = arranged.data();
     const size_t n_chunks = cuts.size() - 1;
     if (c->profiling) {
         // let the host enqueue this call's launches while the GPU idles, so no timed interval contains a wait for
@@ -1221,7 +1244,9 @@ extern "C" void ss_plan_destroy(ss_plan* p) {
 static int plan_build(ss_plan* p, const ss_source* items, int n_items) {
     ss_ctx* c = p->c;
     std::vector<int> cuts;
-    make_chunks(c, items, n_items, cuts);
+    std::vector<ss_source> arranged;
+    arrange_chunks(c, items, n_items, arranged, cuts);
+    items = arranged.data();
     const size_t n_chunks = cuts.size() - 1;
     std::vector<size_t> off(n_chunks + 1, 0);
     size_t scratch_need[ss_ctx::kAux] = {};
