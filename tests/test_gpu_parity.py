@@ -378,3 +378,41 @@ def test_device_path_reports_trajectories_it_cannot_refuse():
     R.render_device([render.MovingSource(x, h2, bounds)], out2)
     with pytest.raises(ValueError):
         R.check_device_errors()
+
+
+def test_fast_kernel_gives_the_same_bits_run_after_run():
+    """k_render_fast hands its buffers over through mbarriers, a cp.async item ring and a last-warp-out election.  A
+    lost hand-over would show as a changed sample: 40 runs of a multi-chunk batch (several items per CTA, X kept and
+    replaced) must all equal the first one bit for bit, and the first must match the oracle."""
+    from sonicsim_b200 import render
+    rng = np.random.default_rng(2024)
+    R = render.default_renderer()
+    R.set_chunk_bytes(24 << 20)
+    try:
+        dev, outs, host = [], [], []
+        for i in range(10):
+            N, P, C, L = 200000 + 4096 * i, 14, 6, 4096
+            x, h = so.synth_dry(rng, N), so.synth_rirs(rng, P, C, L)
+            np.random.seed(300 + i)
+            b = render.trajectory_bounds(so.synth_path(rng, P), N)
+            host.append((x, h, b))
+            dev.append(render.MovingSource(torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda(), torch.from_numpy(b).cuda(), b))
+            outs.append(torch.empty((C, N), device="cuda"))
+        plan = R.plan_device(dev, outs)
+        plan.run()
+        torch.cuda.synchronize()
+        first = [o.clone() for o in outs]
+        for _ in range(40):
+            for o in outs:
+                o.fill_(float("nan"))
+            plan.run()
+            torch.cuda.synchronize()
+            for o, f in zip(outs, first):
+                assert torch.equal(o, f)
+        x, h, b = host[3]
+        idx = np.repeat(np.arange(len(b) - 1), np.diff(b))
+        w = np.concatenate([np.linspace(0, 1, n, endpoint=False) for n in np.diff(b)]).astype(np.float32)
+        assert so.rel_rms(first[3].cpu().numpy(), so.convolve_moving_receiver(x, h, idx, w)) < TOL
+        plan.close()
+    finally:
+        R.set_chunk_bytes(96 << 20)
