@@ -393,8 +393,9 @@ k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr, i
 }
 
 // ----------------------------------------------------------------------------- k_render_fast
-// The all-aligned chunk (every source a compact trajectory with L <= 4096: BASELINE configs[1] / [2]): one item = one
-// transform that packs the positions (s, s + 1) of the block's segment.  Same phases as k_render; what differs is who
+// Chunks whose items are one transform each: compact trajectories under aligned blocking (the transform packs the
+// positions (s, s + 1) of the block's segment) and static sources (two channels per transform), L <= 4096: every source
+// of BASELINE configs[1] / [2] and of a SonicSet scene.  Same phases as k_render; what differs is who
 // feeds the bulk-copy engine and how many bytes pass through the SM's L1 / shared-memory data pipe, which together with
 // the issue slots is what the kernel runs against (profiles/EXPERIMENTS.md):
 //   * a CTA renders a CONTIGUOUS range of items: the channels of a block are neighbours and share the dry spectrum X,
@@ -517,12 +518,12 @@ k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_p
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_item[0] = my_items[0];
         if (n_k > 1) s_item[1] = my_items[grid];
-        const float2* const hp = s_item[0].H0 + (size_t)s_item[0].p_lo * s_item[0].pstride;
+        const float2* const hp = item_hp(s_item[0]);
         fence_proxy_async();
 #if SS_F_XKEEP
         mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
         bulk_g2s(sHp, hp, kSpecBytes, &s_bar[0]);
-        bulk_g2s(sHq, hp + s_item[0].pstride, kSpecBytes, &s_bar[0]);
+        bulk_g2s(sHq, item_hq(s_item[0]), kSpecBytes, &s_bar[0]);
         mbar_expect_tx(&s_bar[1], kSpecBytes);
         bulk_g2s(sX, s_item[0].X, kSpecBytes, &s_bar[1]);
 #else
@@ -530,7 +531,7 @@ k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_p
         bulk_g2s(sX, s_item[0].X, kSpecBytes, &s_bar[0]);
         bulk_g2s(sHp, hp, kSpecBytes, &s_bar[0]);
         mbar_expect_tx(&s_bar[1], kSpecBytes);
-        bulk_g2s(sHq, hp + s_item[0].pstride, kSpecBytes, &s_bar[1]);
+        bulk_g2s(sHq, item_hq(s_item[0]), kSpecBytes, &s_bar[1]);
 #endif
     }
     __syncthreads();
@@ -577,7 +578,7 @@ k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_p
 #else
                 fence_proxy_async();
                 mbar_expect_tx(&s_bar[1], kSpecBytes);
-                bulk_g2s(sHq, nx.H0 + (size_t)(nx.p_lo + 1) * nx.pstride, kSpecBytes, &s_bar[1]);
+                bulk_g2s(sHq, item_hq(nx), kSpecBytes, &s_bar[1]);
 #endif
             }
             // item k + 2 into the slot of item k - 1 (last read in the output stage of k - 1, which every warp has left)
@@ -632,11 +633,11 @@ k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_p
             fence_proxy_async();
             mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
 #if SS_F_XKEEP
-            bulk_g2s(sHp, nx.H0 + (size_t)nx.p_lo * nx.pstride, kSpecBytes, &s_bar[0]);
-            bulk_g2s(sHq, nx.H0 + (size_t)(nx.p_lo + 1) * nx.pstride, kSpecBytes, &s_bar[0]);
+            bulk_g2s(sHp, item_hp(nx), kSpecBytes, &s_bar[0]);
+            bulk_g2s(sHq, item_hq(nx), kSpecBytes, &s_bar[0]);
 #else
             bulk_g2s(sX, nx.X, kSpecBytes, &s_bar[0]);
-            bulk_g2s(sHp, nx.H0 + (size_t)nx.p_lo * nx.pstride, kSpecBytes, &s_bar[0]);
+            bulk_g2s(sHp, item_hp(nx), kSpecBytes, &s_bar[0]);
 #endif
         }
         ph ^= 1;
@@ -1012,7 +1013,8 @@ static void chunk_describe(const ss_source* items, int first, int last, char* hb
         hps[i] = ps;
         ps += spectra_pairs_h(s) + spectra_pairs_x(s) + range_ctas(s);
         pr += sh.max_items;
-        any_long = any_long || s.K > 1; all_aligned = all_aligned && s.aligned;
+        any_long = any_long || s.K > 1;
+        all_aligned = all_aligned && (s.aligned || (s.mode == MODE_STATIC && s.K == 1));      // one transform per item: k_render_fast
     }
     hps[n] = ps;
     // work-item table of the whole chunk (dense) + its length
@@ -1123,8 +1125,9 @@ static void make_chunks(const ss_ctx* c, const ss_source* items, int n, std::vec
     for (int i = 0; i < n; ++i) sb[i] = spectra_bytes(items[i]);
     make_chunks_bytes(sb, budget, cuts);
 }
-// Device path: sources are independent, so a batch is regrouped by the kernel variant its chunk would run - sources
-// under aligned blocking (k_render_fast), long RIRs (k_render<LONG>), everything else (k_render<0, 0>) - and each group
+// Device path: sources are independent, so a batch is regrouped by the kernel variant its chunk would run - one
+// transform per item (aligned moving sources and static ones: k_render_fast), long RIRs (k_render<LONG>), everything
+// else (k_render<0, 0>) - and each group
 // is chunked on its own: one static source no longer sends the moving sources of its chunk through the generic kernel
 // (a SonicSet scene is 3 moving + 2 static sources).  `arranged` receives the regrouped items, `cuts` the chunk bounds.
 static void arrange_chunks(const ss_ctx* c, const ss_source* items, int n, std::vector<ss_source>& arranged, std::vector<int>& cuts) {
@@ -1134,7 +1137,7 @@ static void arrange_chunks(const ss_ctx* c, const ss_source* items, int n, std::
         const int lo = (int)arranged.size();
         for (int i = 0; i < n; ++i) {
             const Shape sh = shape_of(items[i]);
-            const int k = sh.K > 1 ? 1 : (sh.aligned ? 0 : 2);
+            const int k = sh.K > 1 ? 1 : ((sh.aligned || items[i].mode == SS_STATIC) ? 0 : 2);
             if (k == cls) arranged.push_back(items[i]);
         }
         const int cnt = (int)arranged.size() - lo;

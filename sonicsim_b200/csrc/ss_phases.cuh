@@ -131,6 +131,15 @@ SS_HD void fill_items(const Source& s, RItem* items, int blk, const Block& bk, i
     }
 }
 
+// k_render_fast: the two filter spectra of an item's single transform.  Aligned moving source: positions p_lo, p_lo + 1;
+// static source: channels c, c + 1 - a static item without a partner channel reuses the first filter (its imaginary
+// output is not stored).
+SS_HD const float2* item_hp(const RItem& it) { return it.H0 + (size_t)it.p_lo * it.pstride; }
+SS_HD const float2* item_hq(const RItem& it) {
+    const bool has = it.mode == MODE_STATIC ? it.row1 != nullptr : true;
+    return item_hp(it) + (has ? it.pstride : 0);
+}
+
 // transform (item, p) -> descriptor
 SS_HD XDesc make_xdesc(const RItem& it, int p) {
     XDesc d;
@@ -586,6 +595,19 @@ SS_HD void render_epilogue_item(int t, const RItem& it, const Regs32& R) {
     const int nbase = it.n0 + t, n_end = it.n_end;
     float* const row = it.row;
     if (nbase >= n_end) return;
+    if (it.mode == MODE_STATIC) {                            // Re -> channel c, Im -> channel c + 1 (item-uniform branch)
+        float* const row1 = it.row1;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int n = nbase + 256 * r;
+            if (n < n_end) {
+                const float2 z = R.a[out16(r)];
+                row[n] = z.x;
+                if (row1) row1[n] = z.y;
+            }
+        }
+        return;
+    }
     const double d0 = (double)(nbase - it.b0);
     const double step = it.step;
     float w[16];

@@ -190,10 +190,9 @@ static void cta_render_fast(const RItem* items, int n_items, int cta, int grid, 
     s_item[0] = my_items[0];
     if (n_k > 1) s_item[1] = my_items[grid];
     {
-        const float2* hp = s_item[0].H0 + (size_t)s_item[0].p_lo * s_item[0].pstride;
         memcpy(sX, s_item[0].X, sizeof(float2) * kSpec);
-        memcpy(sHp, hp, sizeof(float2) * kSpec);
-        memcpy(sHq, hp + s_item[0].pstride, sizeof(float2) * kSpec);
+        memcpy(sHp, item_hp(s_item[0]), sizeof(float2) * kSpec);
+        memcpy(sHq, item_hq(s_item[0]), sizeof(float2) * kSpec);
     }
     XDesc unused; memset(&unused, 0, sizeof(unused)); unused.kparts = 1;
     std::vector<float2> w(kThreads * 16);
@@ -202,7 +201,7 @@ static void cta_render_fast(const RItem* items, int n_items, int cta, int grid, 
         for (int t = 0; t < kThreads; ++t) { fft16<true>(R[t].a); fft16<true>(R[t].b); }
         if (k + 1 < n_k) {
             const RItem& nx = s_item[(k + 1) % 3];
-            memcpy(sHq, nx.H0 + (size_t)(nx.p_lo + 1) * nx.pstride, sizeof(float2) * kSpec);
+            memcpy(sHq, item_hq(nx), sizeof(float2) * kSpec);
         }
         if (k + 2 < n_k) s_item[(k + 2) % 3] = my_items[(size_t)(k + 2) * grid];
         for (int t = 0; t < kThreads; ++t) { passA_store(fftbuf, passA_jA(t), R[t].a); passA_store(fftbuf, passA_jB(t), R[t].b); }
@@ -217,7 +216,7 @@ static void cta_render_fast(const RItem* items, int n_items, int cta, int grid, 
         if (k + 1 < n_k) {
             const RItem& nx = s_item[(k + 1) % 3];
             memcpy(sX, nx.X, sizeof(float2) * kSpec);
-            memcpy(sHp, nx.H0 + (size_t)nx.p_lo * nx.pstride, sizeof(float2) * kSpec);
+            memcpy(sHp, item_hp(nx), sizeof(float2) * kSpec);
         }
         for (int t = 0; t < kThreads; ++t) {
             float2 (&wt)[16] = *reinterpret_cast<float2 (*)[16]>(&w[16 * t]);
@@ -254,7 +253,7 @@ int emu_render(const float* x, const float* rir, float* out, const int32_t* boun
     const int nr = counts[0] * items_per_block(S);
     const int grid = nr < 3 ? nr : 3;              // a few persistent CTAs, each looping over many items
     for (int cta = 0; cta < grid; ++cta) {
-        if (S.aligned) cta_render_fast(items.data(), nr, cta, grid, T);
+        if (S.aligned || (mode == MODE_STATIC && S.K == 1)) cta_render_fast(items.data(), nr, cta, grid, T);
         else cta_render(items.data(), nr, cta, grid, T, false, S.K > 1);
     }
     return 0;
