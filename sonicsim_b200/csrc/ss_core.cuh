@@ -216,14 +216,6 @@ SS_HD void tw_load_pow(const float2* tab, float2 (&w)[16]) {
 #pragma unroll
     for (int r = 1; r < 8; ++r) w[8 + r] = cmul(w[r], w[8]);
 }
-// all fifteen from w1 alone (already direction-adjusted): w2 = w1^2, w4 = w2^2, w8 = w4^2, the rest products
-SS_HD void tw_from_w1(float2 w1, float2 (&w)[16]) {
-    w[0] = make_float2(1.f, 0.f);
-    w[1] = w1; w[2] = cmul(w1, w1); w[4] = cmul(w[2], w[2]); w[8] = cmul(w[4], w[4]);
-    w[3] = cmul(w[1], w[2]); w[5] = cmul(w[1], w[4]); w[6] = cmul(w[2], w[4]); w[7] = cmul(w[3], w[4]);
-#pragma unroll
-    for (int r = 1; r < 8; ++r) w[8 + r] = cmul(w[r], w[8]);
-}
 template <bool INV>
 SS_HD void fft16_w(float2 (&v)[16], const float2 (&w)[16]) {
     fft4_tw<INV, false>(v[0], v[4], v[8], v[12], w[0], w[4], w[8], w[12]);

@@ -406,65 +406,15 @@ k_render(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr, i
 //   * no serial producer section: work items are final (k_prepare wrote pointers, sample range, segment start and
 //     1 / length) and prefetched two transforms ahead with cp.async;
 //   * inter-pass twiddles: 4 table rows + 11 products per pass (tw_get) instead of 15 loads.
-// Measured and left as knobs (default off): split arrive / wait mbarriers instead of two of the four CTA barriers,
-// twiddle loads hoisted above the exchange barriers, twiddles from registers only - none of them moves the kernel.
-constexpr int kItemLane = 7 * 32;     // thread that prefetches work items and issues the Hq copies (not warp 0, whose
+// Measured and rejected (profiles/EXPERIMENTS.md, profiles/r2_exp_fast_knobs.patch): split arrive / wait mbarriers
+// instead of two of the four CTA barriers, twiddle loads hoisted above the exchange barriers, twiddles from registers
+// only, a fixed producer lane waiting for the buffer - none of them moves the kernel.
+constexpr int kItemLane = 7 * 32;     // thread that prefetches work items and issues the X copies (not warp 0, whose
                                       // thread 0 already carries the DC / Nyquist words)
-// experiment knobs (profiles/EXPERIMENTS.md, round 2)
-#ifndef SS_F_SPLIT
-#define SS_F_SPLIT 0          // 1: split (arrive early / wait late) mbarriers instead of two of the CTA-wide barriers
-#endif
-#ifndef SS_F_HOIST
-#define SS_F_HOIST 0          // 1: inter-pass twiddles loaded ahead of the exchange barrier
-#endif
-#ifndef SS_F_FENCEALL
-#define SS_F_FENCEALL 0       // 1: every thread fences generic -> async proxy before the FFT buffer is handed over
-#endif
-#ifndef SS_F_LATECHECK
-#define SS_F_LATECHECK 0      // 1: the last-warp test (and the X / Hp copy) after the first pass-C butterfly
-#endif
-#ifndef SS_F_TWREG
-#define SS_F_TWREG 0          // 1: no table access inside the loop at all: w1 of pass B and exp(2 pi i t / 8192) live in
-                              //    registers, pass C's w1 is its square (measured: slower, 123 registers; breaks the
-                              //    same-bits-in-every-kernel property of tw_get)
-#endif
-#if SS_F_TWREG
-#define SS_TW_B(w) tw_from_w1(w1b, w)
-#define SS_TW_C(w) tw_from_w1(cmul(wtc, wtc), w)
-#else
-#define SS_TW_B(w) tw_get<true, 16>(T.twB + (t & 15), w)
-#define SS_TW_C(w) tw_get<true, 256>(T.twC + t, w)
-#endif
-#ifndef SS_F_XKEEP
-#define SS_F_XKEEP 1          // 1: a CTA renders a contiguous range of items (the channels of a block are neighbours) and
-                              // keeps the dry spectrum X in its own buffer while consecutive items share it; Hp and Hq
-                              // both land in the FFT buffer
-#endif
-#ifndef SS_F_FAKE
-#define SS_F_FAKE 0           // timing experiments only (WRONG results): 1 no pass B, 2 no staged-spectra reads, 4 no global stores, 8 no bulk copies
-#endif
-#ifndef SS_F_WAITHINT
-#define SS_F_WAITHINT 0       // > 0: suspend-time hint (ns) of the split barriers' try_wait
-#endif
 __device__ __forceinline__ unsigned atom_inc_acqrel(unsigned* p) {
     unsigned old;
     asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
     return old;
-}
-__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
-#if SS_F_WAITHINT > 0
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SS_F_WAITHINT) : "memory");
-#else
-    mbar_wait(bar, parity);
-#endif
 }
 // both butterflies of a thread, the 16 loads of butterfly t first so that its arithmetic can start while the
 // loads of butterfly t + 256 are still in flight
@@ -479,182 +429,88 @@ __global__ void __launch_bounds__(kThreads, SS_RENDER_MINB)
 k_render_fast(const RItem* __restrict__ items, const int* __restrict__ n_items_ptr, int n_items_host) {
     extern __shared__ __align__(128) float2 smem[];
     __shared__ __align__(16) RItem s_item[3];
-    __shared__ __align__(8) uint64_t s_bar[4];          // [0] X + Hp landed, [1] Hq landed (transaction counts);
-                                                        // [2] staged spectra consumed, [3] pass-B inputs loaded (8 warps)
+    __shared__ __align__(8) uint64_t s_bar[2];          // [0] Hp + Hq landed, [1] X landed or kept (transaction counts)
     __shared__ unsigned s_drained;                      // warps that have finished their pass-C loads, cumulative
     float2* const fftbuf = smem;
-#if SS_F_XKEEP
-    float2* const sX = smem + kPadF;                    // its own buffer: survives the transform
-    float2* const sHp = smem;
+    float2* const sHp = smem;                           // the filter spectra land in the FFT buffer itself
     float2* const sHq = smem + kSpec;
-#else
-    float2* const sX = smem;
-    float2* const sHp = smem + kSpec;
-    float2* const sHq = smem + kPadF;
-#endif
+    float2* const sX = smem + kPadF;                    // the dry spectrum has its own buffer: it survives the transform
     const Tables T{g_tw, g_twB, g_twC};
     const int t = threadIdx.x, lane = t & 31;
     // table length: known on the host when it built the tables, otherwise written by k_blocks
     const int n_items = n_items_host >= 0 ? n_items_host : *n_items_ptr;
-#if SS_F_XKEEP
     const int per = n_items / (int)gridDim.x, rem = n_items % (int)gridDim.x;
     const int n_k = per + ((int)blockIdx.x < rem ? 1 : 0);              // transforms of this CTA: a contiguous range
-    const int grid = 1;                                                 // distance between this CTA's items
     if (n_k <= 0) return;
     const RItem* const my_items = items + (size_t)blockIdx.x * per + ((int)blockIdx.x < rem ? (int)blockIdx.x : rem);
-#else
-    const int grid = (int)gridDim.x;
-    const int n_k = (n_items - (int)blockIdx.x + grid - 1) / grid;      // transforms of this CTA
-    if (n_k <= 0) return;
-    const RItem* const my_items = items + blockIdx.x;
-#endif
 
     if (t == kItemLane) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
-        mbar_init(&s_bar[2], kThreads / 32);
-        mbar_init(&s_bar[3], kThreads / 32);
         s_drained = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_item[0] = my_items[0];
-        if (n_k > 1) s_item[1] = my_items[grid];
-        const float2* const hp = item_hp(s_item[0]);
+        if (n_k > 1) s_item[1] = my_items[1];
         fence_proxy_async();
-#if SS_F_XKEEP
         mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
-        bulk_g2s(sHp, hp, kSpecBytes, &s_bar[0]);
+        bulk_g2s(sHp, item_hp(s_item[0]), kSpecBytes, &s_bar[0]);
         bulk_g2s(sHq, item_hq(s_item[0]), kSpecBytes, &s_bar[0]);
         mbar_expect_tx(&s_bar[1], kSpecBytes);
         bulk_g2s(sX, s_item[0].X, kSpecBytes, &s_bar[1]);
-#else
-        mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
-        bulk_g2s(sX, s_item[0].X, kSpecBytes, &s_bar[0]);
-        bulk_g2s(sHp, hp, kSpecBytes, &s_bar[0]);
-        mbar_expect_tx(&s_bar[1], kSpecBytes);
-        bulk_g2s(sHq, item_hq(s_item[0]), kSpecBytes, &s_bar[1]);
-#endif
     }
     __syncthreads();
 
     Regs32 R;
     float2 w[16];
-#if SS_F_TWREG
-    const float2 wtc = dirw<true>(ldg_cached(T.tw + t));                     // exp(+2 pi i t / 8192): closing radix-2, and w1 of pass C squared
-    const float2 w1b = dirw<true>(ldg_cached(T.twB + 16 + (t & 15)));       // exp(+2 pi i (t & 15) / 256): w1 of pass B
-#endif
     XDesc unused; unused.kparts = 1; unused.Hq = nullptr; unused.X = nullptr; unused.Hp = nullptr;
     unsigned ph = 0;
     for (int k = 0; k < n_k; ++k) {
-#if !(SS_F_FAKE & 8)
         mbar_wait(&s_bar[0], ph);
         mbar_wait(&s_bar[1], ph);
-#endif
-#if SS_F_FAKE & 2
-#pragma unroll
-        for (int r = 0; r < 16; ++r) { R.a[r] = make_float2(1.f + r + t, 2.f * r - k); R.b[r] = make_float2(0.5f * r + k, 3.f - t); }
-#else
         form_z<false, true>(t, sX, sHp, sHq, unused, R);
-#endif
-#if SS_F_SPLIT
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_bar[2]);            // this warp no longer reads the staged spectra
         fft16<true>(R.a);
         fft16<true>(R.b);
-        mbar_wait_hint(&s_bar[2], ph);                    // ... and neither does any other: pass A may overwrite X / Hp
-#else
-        fft16<true>(R.a);
-        fft16<true>(R.b);
-        __syncthreads();
-#endif
+        __syncthreads();                                  // B1: staged spectra consumed, pass A may overwrite Hp / Hq
         if (t == kItemLane) {
-            if (k + 1 < n_k && !(SS_F_FAKE & 8)) {        // Hq of transform k + 1 (its item became visible at barrier B4 of k - 1)
+            if (k + 1 < n_k) {                            // item k + 1 became visible at barrier B4 of transform k - 1
                 const RItem& nx = s_item[(k + 1) % 3];
-#if SS_F_XKEEP
                 if (nx.X != s_item[k % 3].X) {            // next item belongs to another block: its dry spectrum
                     fence_proxy_async();
                     mbar_expect_tx(&s_bar[1], kSpecBytes);
                     bulk_g2s(sX, nx.X, kSpecBytes, &s_bar[1]);
                 } else mbar_arrive(&s_bar[1]);            // same block, other channel: X stays where it is
-#else
-                fence_proxy_async();
-                mbar_expect_tx(&s_bar[1], kSpecBytes);
-                bulk_g2s(sHq, item_hq(nx), kSpecBytes, &s_bar[1]);
-#endif
             }
             // item k + 2 into the slot of item k - 1 (last read in the output stage of k - 1, which every warp has left)
-            if (k + 2 < n_k) item_prefetch(&s_item[(k + 2) % 3], my_items + (size_t)(k + 2) * grid);
+            if (k + 2 < n_k) item_prefetch(&s_item[(k + 2) % 3], my_items + (k + 2));
         }
         passA_store(fftbuf, passA_jA(t), R.a);
         passA_store(fftbuf, passA_jB(t), R.b);
-#if SS_F_HOIST
-        SS_TW_B(w);
-#endif
-#if !(SS_F_FAKE & 1)
         __syncthreads();                                  // B2: pass A -> pass B exchange
         load2_ab(t, fftbuf, R);
-#if !SS_F_HOIST
-        SS_TW_B(w);
-#endif
-#if SS_F_SPLIT
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_bar[3]);
+        tw_get<true, 16>(T.twB + (t & 15), w);
         fft16_w<true>(R.a, w);
         fft16_w<true>(R.b, w);
-        mbar_wait_hint(&s_bar[3], ph);                    // every warp has loaded its pass-B inputs
-#else
-        fft16_w<true>(R.a, w);
-        fft16_w<true>(R.b, w);
-        __syncthreads();
-#endif
+        __syncthreads();                                  // B3: every warp has loaded its pass-B inputs
         passB_store(fftbuf, t, R.a);
         passB_store(fftbuf, t + 256, R.b);
-#endif
-#if SS_F_HOIST
-        SS_TW_C(w);
-#endif
         if (t == kItemLane) item_prefetch_wait();         // item k + 2 has landed; visible to all behind B4
         __syncthreads();                                  // B4: pass B -> pass C exchange
         load2_ab(t, fftbuf, R);
-#if !SS_F_HOIST
-        SS_TW_C(w);
-#endif
-#if SS_F_FENCEALL
-        fence_proxy_async();
-#endif
+        tw_get<true, 256>(T.twC + t, w);
         __syncwarp();
-        unsigned drained = 0;
-        if (lane == 0) drained = atom_inc_acqrel(&s_drained);
-#if SS_F_LATECHECK
-        fft16_w<true>(R.a, w);                            // pass C, first butterfly
-#endif
-        if (lane == 0 && drained == (unsigned)(8 * k + 7) && k + 1 < n_k && !(SS_F_FAKE & 8)) {
-            // last warp out of the FFT buffer: stage X, Hp of transform k + 1 into it
+        if (lane == 0 && atom_inc_acqrel(&s_drained) == (unsigned)(8 * k + 7) && k + 1 < n_k) {
+            // last warp out of the FFT buffer: stage Hp, Hq of transform k + 1 into it
             const RItem& nx = s_item[(k + 1) % 3];
             fence_proxy_async();
             mbar_expect_tx(&s_bar[0], 2 * kSpecBytes);
-#if SS_F_XKEEP
             bulk_g2s(sHp, item_hp(nx), kSpecBytes, &s_bar[0]);
             bulk_g2s(sHq, item_hq(nx), kSpecBytes, &s_bar[0]);
-#else
-            bulk_g2s(sX, nx.X, kSpecBytes, &s_bar[0]);
-            bulk_g2s(sHp, item_hp(nx), kSpecBytes, &s_bar[0]);
-#endif
         }
         ph ^= 1;
-#if !SS_F_LATECHECK
         fft16_w<true>(R.a, w);                            // pass C
-#endif
         fft16_w<true>(R.b, w);
-#if SS_F_TWREG
-        render_phase3_close_w(R, wtc);
-#else
         render_phase3_close(t, R, T);
-#endif
-#if SS_F_FAKE & 4
-        if (R.a[0].x + R.a[5].y + R.a[9].x + R.a[15].y == 123.456f) render_epilogue_item(t, s_item[k % 3], R);
-#else
         render_epilogue_item(t, s_item[k % 3], R);
-#endif
     }
 }
 

@@ -481,16 +481,7 @@ SS_HD void render_phase3(int t, Regs32& R, const Tables& T) {
         R.a[sl] = cfms(R.a[sl], u[r], R.b[sl]);
     }
 }
-// the closing radix-2 alone (pass C already done by the caller); wt = exp(+2 pi i t / 8192)
-SS_HD void render_phase3_close_w(Regs32& R, float2 wt) {
-    float2 u[16];
-    final_twiddles<true>(wt, u);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        const int sl = out16(r);
-        R.a[sl] = cfms(R.a[sl], u[r], R.b[sl]);
-    }
-}
+// the closing radix-2 alone (pass C already done by the caller)
 SS_HD void render_phase3_close(int t, Regs32& R, const Tables& T) {
     float2 u[16];
     final_twiddles<true>(dirw<true>(ldg_cached(T.tw + t)), u);
